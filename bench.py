@@ -1,0 +1,288 @@
+#!/usr/bin/env python
+"""bench.py -- VB iterations of the NBMF hot path on B200 (BASELINE.json metric:
+VB iters/s and entries*K/s, with % of roofline, beside the CPU reference path).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c5|c4|mid|c1] [--impl reference]
+
+A "step" is one VB_aspect iteration (parameter kernels + both contraction passes +
+the F x K exchange when sharded) over the whole synthetic DirBer matrix, generated
+on the device (R/utils.R:7-16 generator).  Under torchrun the N columns are sharded
+across ranks (strong scaling: total work fixed).  Rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: F, N, K, Ktrue, gamma, description
+    "c5": dict(F=262144, N=262144, K=128, Kt=8, gamma=1.0 / 128, a=1.0, b=1.0, seed=5,
+               desc="VB_aspect contraction, synthetic DirBer 262144x262144, K=128 (BASELINE configs[4])"),
+    "c4": dict(F=65536, N=65536, K=64, Kt=8, gamma=1.0, a=1.0, b=1.0, seed=4,
+               desc="VB_aspect, synthetic DirBer 65536x65536, K=64 (BASELINE configs[3])"),
+    "mid": dict(F=16384, N=16384, K=128, Kt=8, gamma=1.0 / 128, a=1.0, b=1.0, seed=6,
+                desc="VB_aspect, synthetic DirBer 16384x16384, K=128"),
+    "c1": dict(F=200, N=300, K=3, Kt=3, gamma=1.0, a=0.1, b=0.1, seed=1,
+               desc="VB_aspect, synthetic DirBer 200x300, K=3 (BASELINE configs[0] shape)"),
+}
+METRIC = "vb_entries_K_per_s"
+UNIT = "entries*K/s"
+
+
+def read_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d.get("hbm_gbs", 6650.0), bf16_burst=d.get("bf16_tflops", 1590.0),
+                    bf16_sustained=d.get("bf16_tflops_sustained", 1400.0), source="measured")
+    return dict(hbm=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = False
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                self.samples.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0])); mx.append(float(s[1]))
+                for nm, v in zip(names, s[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_run(wl, steps, warmup, sample_F=1024, sample_N=1024):
+    """The reference's CPU path (oracle/_ref if built, else the oracle port), 1 thread
+    (the reference is single-threaded), on a bounded sample of the workload."""
+    from oracle import oracle
+    K = wl["K"]
+    F = min(sample_F, wl["F"]); N = min(sample_N, wl["N"])
+    V, _, _ = oracle.generate(F, N, wl["Kt"], wl["a"], wl["b"], wl["seed"])
+    Z = oracle.random_labels(V, K, wl["seed"] + 1)
+    kind = "port"
+    fn = lambda it: oracle.vb_aspect(V, Z, K, 1.0, 1.0, wl["gamma"], iter=it, checklb=False)
+    try:
+        from oracle import ref as oref
+        if oref.available():
+            kind = "reference"
+            fn = lambda it: oref.vb_aspect(V, Z, K, 1.0, 1.0, wl["gamma"], iter=it, checklb=False)
+    except Exception:
+        pass
+    # the oracle call includes the one-hot E_Z init (as the reference does); time a
+    # warmup-iteration call and a (warmup+steps)-iteration call and take the difference
+    t0 = time.perf_counter(); fn(max(warmup, 1)); t1 = time.perf_counter()
+    fn(max(warmup, 1) + steps); t2 = time.perf_counter()
+    dt = max((t2 - t1) - (t1 - t0), 1e-9)
+    val = F * N * K * steps / dt
+    return dict(value=val, unit=UNIT, cores=1, kind=kind,
+                sample=f"{F}x{N} synthetic DirBer (same generator), K={K}, {steps} sequential VB_Aspect_Rcpp "
+                       f"iterations, 1 thread (the reference has no threading); host has {os.cpu_count()} cores"), dt
+
+
+def run_reference(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 10))
+    cb, dt = cpu_reference_run(wl, steps, min(args.warmup, 2))
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": steps, "warmup": min(args.warmup, 2), "ms_per_step": 1e3 * dt / steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": wl["desc"], "F": wl["F"], "N": wl["N"], "K": wl["K"]},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def tensor_from_ptr(ptr, count, device):
+    import torch
+
+    class _Arr:
+        pass
+    a = _Arr()
+    a.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+    return torch.as_tensor(a, device=device)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("NBMF_BENCH_WORKLOAD", "c5"), choices=list(WORKLOADS))
+    ap.add_argument("--precision", type=int, default=0, help="nbmf_precision (0 auto, 1 fp64, 2 tensor, 3 tensor-full)")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    wl = dict(WORKLOADS[args.workload])
+    if args.impl == "reference":
+        run_reference(args, wl)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from nbmf_b200 import Engine
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    F, N, K = wl["F"], wl["N"], wl["K"]
+    n_lo = (N * rank) // world; n_hi = (N * (rank + 1)) // world
+    Nl = n_hi - n_lo
+
+    eng = Engine(device=local, precision=args.precision, n_global=N if world > 1 else 0, n_offset=n_lo)
+    eng.generate_synthetic(F, Nl, wl["Kt"], wl["a"], wl["b"], wl["seed"])
+    if world > 1:
+        def hook(ptr, count, stream):
+            t = tensor_from_ptr(ptr, count, dev)
+            with torch.cuda.stream(torch.cuda.ExternalStream(stream, device=dev)):
+                dist.all_reduce(t)
+        eng.set_allreduce_hook(hook)
+    eng.init_random_labels(K, wl["seed"] + 1)
+    ext = torch.cuda.ExternalStream(eng.stream, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    eng.vb_begin(K, 1.0, 1.0, wl["gamma"])
+    for _ in range(max(args.warmup, 3)):
+        eng.vb_step(False)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start(); time.sleep(0.25)
+    t_launch0 = eng.timing()["launches"]
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(ext)
+    for _ in range(args.steps):
+        eng.vb_step(False)
+    e1.record(ext)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    tim = eng.timing()
+    launches = tim["launches"] - t_launch0
+    clocks = sampler.finish() if sampler else None
+    eng.vb_end(0, want_outputs=False)
+    tim = eng.timing()  # phase split of the last iteration (CUDA events on the engine's stream)
+    if world > 1:
+        t = torch.tensor([ms, tim["pass_rows_ms"] + tim["pass_cols_ms"]], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, pass_ms = t[0].item(), t[1].item()
+    else:
+        pass_ms = tim["pass_rows_ms"] + tim["pass_cols_ms"]
+    value = F * N * K * args.steps / (ms * 1e-3)
+
+    # ---- e2e: host buffers through the C ABI, H2D + D2H inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        v, m = eng.get_data_bits(want_mask=False)
+        pv = torch.empty(v.shape, dtype=torch.int32, pin_memory=True)
+        pv.numpy().view(np.uint32)[...] = v
+        vb_host = pv.numpy().view(np.uint32)
+        del v, m
+        eng.init_random_labels(K, wl["seed"] + 1)
+        st = eng.get_stats(K)
+        steps_e = max(1, args.e2e_steps)
+        h2d = vb_host.nbytes + sum(x.nbytes for x in st)
+        d2h = (F * K + Nl * K) * 8 + 8
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps_e):
+            eng.set_data_bits(vb_host, None, F, Nl)
+            eng.set_stats(*st)
+            eng.vb_aspect(K, 1.0, 1.0, wl["gamma"], iter=1, checklb=True)
+        barrier()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = t.item()
+        e2e = {"value": F * N * K * steps_e / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "steps": steps_e, "ms_per_step": 1e3 * dt / steps_e,
+               "what": "per step: nbmf_set_data_bits(host V bits) + nbmf_set_stats(host) + nbmf_vb_aspect(iter=1, checklb) -> host E_W, E_H, ELBO"}
+
+    if rank == 0:
+        peaks = read_peaks()
+        flops = 12.0 * F * Nl * K  # 12 flop per entry*K per iteration (this rank's columns)
+        ach = flops / (pass_ms * 1e-3) / 1e12 if pass_ms > 0 else 0.0
+        peak = peaks["bf16_sustained"]
+        roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                "traffic": None, "peak_source": f"{peaks['source']} bf16 sustained (MEASURED_PEAKS.json)",
+                "kernel": "contraction passes (rows + cols) of one iteration, CUDA events inside libnbmf_cuda",
+                "pass_rows_ms": tim["pass_rows_ms"], "pass_cols_ms": tim["pass_cols_ms"],
+                "params_ms": tim["params_ms"], "exchange_ms": tim["exchange_ms"],
+                "frac_of_tf32_nominal_half": ach / (peak / 2.0)}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "iters_per_s": args.steps / (ms * 1e-3),
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f64" if (args.precision == 1 or (args.precision == 0 and K < 32)) else "f16x2-split/f32-accum",
+                "data": "synthetic",
+                "config": {"workload": wl["desc"], "F": F, "N": N, "K": K, "columns_per_rank": Nl,
+                           "l2_policy": "inputs larger than L2 (bit planes + operands stream from HBM)"
+                           if F * N / 8 > 126e6 else "inputs smaller than L2; no flush (latency-sized config)"},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof}
+        if world == 1 and not args.no_cpu_baseline:
+            cb, _ = cpu_reference_run(wl, 3, 1)
+            line["cpu_baseline"] = cb
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

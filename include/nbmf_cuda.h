@@ -1,0 +1,192 @@
+/*
+ * nbmf_cuda.h -- C ABI of libnbmf_cuda, the B200 (sm_100a) engine for the
+ * data-parallel hot path of alumbreras/NBMF (R package rMMLEDirBer).
+ *
+ * The library replaces the *bodies* of the reference's Rcpp hot functions; the
+ * R entry point BernoulliNMF() (R/BernoulliNMF.R:12-106), the generated glue
+ * (src/RcppExports.cpp:259-344, R/RcppExports.R:4-86) and the C++ signatures
+ * stay as they are.  INTEGRATION.md shows the marshalling bodies.
+ *
+ * Conventions (the reference's own):
+ *   - host matrices are column-major; V and Z are int32, NA = INT_MIN
+ *     (R's NA_INTEGER; tested as V(f,n) != NA_INTEGER at
+ *     collapsed_gibbs_z_VB.cpp:56,124,449); Z labels are 0-based, NA where V
+ *     is NA; every output is host fp64 column-major, caller-owned.
+ *   - V is F x N.  W is the Dirichlet factor (F x K, rows sum to 1), H the
+ *     Beta factor (N x K), as VB_Aspect_Rcpp returns them
+ *     (collapsed_gibbs_z_VB.cpp:507-525).
+ *   - every function returns 0 on success or a negative nbmf_status;
+ *     nbmf_last_error() gives the message the Rcpp body passes to Rcpp::stop().
+ *     The library never calls R, never throws, never prints.
+ *   - there is no CPU fallback: without a CUDA device every compute entry
+ *     point fails with NBMF_ERR_CUDA.
+ */
+#ifndef NBMF_CUDA_H
+#define NBMF_CUDA_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NBMF_NA_INTEGER INT32_MIN
+
+typedef enum nbmf_status {
+    NBMF_OK = 0,
+    NBMF_ERR_ARG = -1,     /* bad argument (the reference would index out of bounds) */
+    NBMF_ERR_CUDA = -2,    /* CUDA runtime / driver error, no device, wrong arch     */
+    NBMF_ERR_STATE = -3,   /* call order (no data, no statistics, ...)               */
+    NBMF_ERR_NEGATIVE = -4,/* the reference's "Negative values in ..." stop()        */
+    NBMF_ERR_OOM = -5,
+    NBMF_ERR_UNSUPPORTED = -6
+} nbmf_status;
+
+/* which arithmetic the contraction kernel uses */
+typedef enum nbmf_precision {
+    NBMF_PREC_AUTO = 0,        /* FP64 FMA path for K < 32, tensor path otherwise        */
+    NBMF_PREC_FP64 = 1,        /* FP64 FMA + warp shuffles (any K <= 512)                 */
+    NBMF_PREC_TENSOR = 2,      /* tcgen05 f16 hi/lo split, fp32 accumulate in TMEM        */
+    NBMF_PREC_TENSOR_FULL = 3  /* tensor path, every operand split (3+2 passes)           */
+} nbmf_precision;
+
+/* VB_DirBer_Rcpp modes */
+typedef enum nbmf_dirber_mode {
+    NBMF_DIRBER_EXACT_WAVEFRONT = 0, /* bit-identical schedule to collapsed_gibbs_z_VB.cpp:119-141 */
+    NBMF_DIRBER_CONTRACTION = 1      /* self-term-free batch form        */
+} nbmf_dirber_mode;
+
+typedef struct nbmf_opts {
+    int device;          /* CUDA ordinal                                                    */
+    int precision;       /* nbmf_precision                                                  */
+    int flush_interval;  /* tensor path: steps between TMEM accumulator flushes; 0 = default */
+    int reserved0;
+    int64_t n_global;    /* column sharding: total number of columns (0 = not sharded)      */
+    int64_t n_offset;    /* first global column this handle owns                            */
+} nbmf_opts;
+
+typedef struct nbmf_handle nbmf_handle;
+
+/* collective hook: called on the exchange step of each iteration with a device
+ * buffer the caller must sum across ranks in place (count elements of fp64),
+ * enqueued on `stream` (a cudaStream_t).  Return 0 on success.  This is the only
+ * data-path collective: the F x K Dirichlet-side statistic.     */
+typedef int (*nbmf_allreduce_fn)(void *ctx, void *device_buf, size_t count, void *stream);
+
+/* timing of the last VB / Gibbs call, CUDA events on the handle's stream */
+typedef struct nbmf_timing {
+    double total_ms;        /* iteration loop only (no H2D / D2H / packing)  */
+    double params_ms;
+    double pass_rows_ms;    /* owner = rows f (Dirichlet-side statistic)     */
+    double pass_cols_ms;    /* owner = columns n (Beta-side statistics)      */
+    double exchange_ms;
+    int64_t launches;       /* kernels launched inside the loop              */
+    int64_t iters;
+} nbmf_timing;
+
+const char *nbmf_version(void);
+int nbmf_device_count(void);
+
+int nbmf_create(nbmf_handle **out, const nbmf_opts *opts);
+void nbmf_destroy(nbmf_handle *h);
+const char *nbmf_last_error(const nbmf_handle *h);
+void *nbmf_stream(nbmf_handle *h); /* cudaStream_t the handle launches on */
+int nbmf_synchronize(nbmf_handle *h);
+int nbmf_set_allreduce_hook(nbmf_handle *h, nbmf_allreduce_fn fn, void *ctx);
+int nbmf_get_timing(const nbmf_handle *h, nbmf_timing *out);
+
+/* ---- data ---------------------------------------------------------------
+ * replaces: `const arma::imat& V` argument of VB_Aspect_Rcpp / VB_DirBer_Rcpp /
+ * Gibbs_DirBer_finite_Rcpp (collapsed_gibbs_z_VB.cpp:373,97;
+ * collapsed_gibbs_z.cpp:363).  Packs V into a value-bit plane and a mask-bit
+ * plane on the device (2 bits per entry), in both column- and row-packed form. */
+int nbmf_set_data_i32(nbmf_handle *h, const int32_t *V_colmajor, int64_t F, int64_t N);
+/* already-packed input: bit f of column n is bit (f & 31) of word
+ * vbits[n * ceil(F/32) + (f >> 5)]; mbits == NULL means no NA.               */
+int nbmf_set_data_bits(nbmf_handle *h, const uint32_t *vbits, const uint32_t *mbits, int64_t F,
+                       int64_t N);
+/* synthetic DirBer matrix generated on the device (R/utils.R:7-16 sample_V,
+ * experiments/xp_paper_basic_example.R:22-30): W_f ~ Dir(a 1), H_nk ~ Beta(a,b),
+ * V_fn ~ Bernoulli(W_f . H_n); Philox4x32-10 keyed (seed, f, global n) so every
+ * sharding produces the same matrix.  N = local columns.                      */
+int nbmf_generate_synthetic(nbmf_handle *h, int64_t F, int64_t N, int Ktrue, double a, double b,
+                            uint64_t seed);
+int nbmf_get_dims(const nbmf_handle *h, int64_t *F, int64_t *N, int64_t *nobs);
+/* column-packed planes back to the host (for tests and checkpoints) */
+int nbmf_get_data_bits(nbmf_handle *h, uint32_t *vbits, uint32_t *mbits);
+
+/* ---- initial statistics ---------------------------------------------------
+ * replaces vb_matrix_to_tensor + compute_vbcounts (commons.cpp:29-42,
+ * collapsed_gibbs_z_VB.cpp:42-66) and compute_counts (collapsed_gibbs_z.cpp:
+ * 38-60): a histogram of the labels, no F x K x N tensor.                     */
+int nbmf_init_from_labels(nbmf_handle *h, const int32_t *Z_colmajor, int Kc);
+/* Z_fn = Philox(seed, f, global n) mod Kc on the device (BernoulliNMF.R:23-33
+ * draws sample(K_init,1) per observed entry)                                  */
+int nbmf_init_random_labels(nbmf_handle *h, int Kc, uint64_t seed);
+/* n_total F x Kc, f_ones N x Kc, f_zeros N x Kc (vbcounts,
+ * collapsed_gibbs_z_VB.cpp:14-35); also the checkpoint / resume state.        */
+int nbmf_set_stats(nbmf_handle *h, int Kc, const double *n_total, const double *f_ones,
+                   const double *f_zeros);
+int nbmf_get_stats(nbmf_handle *h, int Kc, double *n_total, double *f_ones, double *f_zeros);
+
+/* ---- VB_Aspect_Rcpp (collapsed_gibbs_z_VB.cpp:373-526) ---------------------
+ * iter batch iterations; E_W F x K, E_H N x K from the parameters at the top of
+ * the last iteration (:507-514); lowerbounds[iter] (0 when !checklb, :474-477);
+ * E_Z (F x K x N, arma::cube layout) only if non-NULL.
+ * Requires data + initial statistics with Kc == K.                            */
+int nbmf_vb_aspect(nbmf_handle *h, int K, double alpha, double beta, double gamma, int iter,
+                   int checklb, double *E_W, double *E_H, double *lowerbounds, double *E_Z);
+/* the same, one iteration at a time (what bench.py times):
+ *   begin -> step x iter -> end                                               */
+int nbmf_vb_begin(nbmf_handle *h, int K, double alpha, double beta, double gamma, int mean_params);
+int nbmf_vb_step(nbmf_handle *h, int checklb);
+int nbmf_vb_end(nbmf_handle *h, double *E_W, double *E_H, double *lowerbounds, int n_lb,
+                double *E_Z);
+/* ELBO split of the last VB session, 3 doubles per iteration: sum_obs log D over
+ * the handle's columns, pW - qW (rows: replicated under column sharding),
+ * pH - qH (the handle's columns).  lowerbounds[i] of nbmf_vb_end is their sum. */
+int nbmf_vb_get_lb_terms(nbmf_handle *h, double *terms3, int n_iter);
+
+/* ---- lower_bound_aspect (collapsed_gibbs_z_VB.cpp:339-369) -----------------
+ * ELBO of the current statistics' parameters with q(Z) at its optimum, and its
+ * seven-term split (pW,pZ+pV-qZ,pH,0,qW,0,qH) for diagnostics.                */
+int nbmf_lower_bound(nbmf_handle *h, int K, double alpha, double beta, double gamma, double *lb,
+                     double *terms7);
+
+/* ---- VB_DirBer_Rcpp (collapsed_gibbs_z_VB.cpp:97-168) ----------------------
+ * Kc = K+1 columns in E_W (F x (K+1)) and E_H (N x (K+1)); iter-1 sweeps.
+ * EXACT_WAVEFRONT needs the labels (call nbmf_init_from_labels with Kc = K+1
+ * first; the engine keeps them) and materialises E_Z on the device.           */
+int nbmf_vb_dirber(nbmf_handle *h, int K, double alpha, double beta, double gamma, int iter,
+                   int mode, double *E_W, double *E_H, double *E_Z);
+
+/* ---- Gibbs (collapsed_gibbs_z.cpp:363-437 + :565-605; R/MCEM - sample_gibbs.R
+ * :40-77) -- uncollapsed blocked sweep  Z|W,H -> counts -> W|Z, H|Z,V.
+ * iter-1 sweeps, kept when i >= floor(iter*burnin).  E_W / E_H are the
+ * Rao-Blackwell posterior means of expectation.GibbsDirBer
+ * (R/generic_Gibbs_DirBer.R:54-101).  test_idx: n_test linear indices
+ * f + F*n of held-out entries; E_V_test[n_test] receives mean_j (E_W E_H^T)
+ * there.  Z_last (F x N) receives the last assignment.                        */
+int nbmf_gibbs_dirber(nbmf_handle *h, int K, double alpha, double beta, double gamma, int iter,
+                      double burnin, uint64_t seed, double *E_W, double *E_H,
+                      const int64_t *test_idx, int64_t n_test, double *E_V_test, int32_t *Z_last);
+
+/* one column's sweep given a fixed dictionary (sample_gibbs.cpp:22-80,
+ * R sample_gibbs_ZH): v_n[F] in {0,1}, W F x K (paper orientation: Beta means),
+ * returns the mean one-hot assignment C_mean F x K over kept sweeps.          */
+int nbmf_gibbs_sweep_given_W(nbmf_handle *h, const int32_t *v_n, const double *W, int64_t F,
+                             int K, double alpha, int iter, double burnin, uint64_t seed,
+                             double *C_mean);
+
+/* ---- loglikelihood.Bernoulli (R/commons.R:17-33) ---------------------------
+ * sum over non-NA entries of V_test of log(v p + (1-v)(1-p)), p = E_W E_H^T,
+ * without forming F x N.                                                      */
+int nbmf_predictive_ll(nbmf_handle *h, const double *E_W, const double *E_H, int K,
+                       const int32_t *V_test_colmajor, int64_t F, int64_t N, double *ll,
+                       int64_t *n_test);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NBMF_CUDA_H */

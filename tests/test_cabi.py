@@ -1,0 +1,60 @@
+"""CPU-side checks of the drop-in boundary: the shared library loads, exports
+every symbol include/nbmf_cuda.h declares, and refuses to compute without a GPU
+(no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from nbmf_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "nbmf_cuda.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = re.findall(r"\b(nbmf_[a-z0-9_]+)\s*\(", src, flags=re.I)
+    return sorted({n for n in names if n not in ("nbmf_allreduce_fn",)})
+
+
+def test_header_symbols_are_exported_and_bound():
+    lib = _lib.load()
+    decl = declared_symbols()
+    assert len(decl) >= 25
+    for name in decl:
+        assert hasattr(lib, name), f"{name} declared in include/nbmf_cuda.h but not exported"
+    # the ctypes table covers the header exactly
+    assert sorted(_lib.SYMBOLS) == decl
+
+
+def test_version_and_no_fortran_names():
+    lib = _lib.load()
+    assert b"sm_100a" in lib.nbmf_version()
+
+
+def test_create_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib = _lib.load()
+    assert lib.nbmf_device_count() == 0
+    h = C.c_void_p()
+    rc = lib.nbmf_create(C.byref(h), None)
+    assert rc == -2 and not h  # NBMF_ERR_CUDA, no handle, no fallback
+    from nbmf_b200 import Engine, NbmfError
+    with pytest.raises(NbmfError):
+        Engine()
+
+
+def test_product_package_never_uses_oracle():
+    """The oracle is test infrastructure: nothing shipped may import, include or link it."""
+    pkg = os.path.join(ROOT, "nbmf_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if not fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp", "Makefile")):
+                continue
+            txt = open(os.path.join(dirpath, fn), errors="ignore").read()
+            assert "import oracle" not in txt and "from oracle" not in txt, fn
+            assert "oracle/" not in txt and "nbmf_oracle" not in txt and "libnbmf_ref" not in txt, fn
