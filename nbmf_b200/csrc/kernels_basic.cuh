@@ -61,6 +61,14 @@ __global__ void transpose_bits_kernel(const uint32_t *__restrict__ src, int64_t 
     if (c < C) dst[c * Wd + g] = keep;
 }
 
+__global__ void popcount_kernel(const uint32_t *__restrict__ m, int64_t count, unsigned long long *out)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned c = (i < count) ? __popc(m[i]) : 0u;
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, (unsigned long long)c);
+}
+
 // fill the mask planes for data without NA: bit set iff index < limit
 __global__ void fill_mask_kernel(uint32_t *m, int64_t rows, int64_t words, int64_t limit)
 {
@@ -182,7 +190,7 @@ __global__ void rows_to_colmajor_kernel(const double *__restrict__ src, int64_t 
 //     alpha_vb = alpha + f_ones, beta_vb = beta + f_zeros
 //     B1 = exp(psi(alpha_vb) - psi(alpha_vb+beta_vb)), B0 likewise with beta_vb
 //   mean mode (CVB0 without the self term):
-//     A = gamma_vb, B1 = alpha_vb/(alpha_vb+beta_vb), B0 = beta_vb/(...)
+//     A = gamma_vb / sum_k gamma_vb (the row scale cancels in E_Z), B1 = alpha_vb/(alpha_vb+beta_vb), B0 = beta_vb/(...)
 //   E_W = gamma_vb / sum_k gamma_vb, E_H = alpha_vb/(alpha_vb+beta_vb) (:507-514)
 //   want_lb: adds pW - qW (rows) / pH - qH (columns) to scal[SC_PRIOR]
 //   (E_log_p_W_Rcpp :173-182, E_log_q_W_Rcpp :185-197, E_log_p_H_Rcpp :243-253,
@@ -208,7 +216,7 @@ __global__ void params_rows_kernel(const double *__restrict__ statF, int64_t F, 
                 double g = gamma + statF[f * Kp + k];
                 if (g < 0) neg = 1.0;
                 double elw = dev_digamma(g) - ps;
-                A[f * Kp + k] = mean_mode ? g : exp(elw);
+                A[f * Kp + k] = mean_mode ? g / s : exp(elw); // mean mode: E_W, so that D <= 1 in both modes
                 EW[f * Kp + k] = g / s;
                 if (want_lb) { sum_elw += elw; q += -lgamma(g) + (g - 1.0) * elw; }
             } else {

@@ -228,8 +228,15 @@ extern "C" int nbmf_set_data_bits(nbmf_handle *h, const uint32_t *vbits, const u
     if (mbits) {
         CK(cudaMemcpy2DAsync(h->mc, (size_t)h->Fw * 4, mbits, (size_t)fw_in * 4, (size_t)fw_in * 4,
                              (size_t)N, cudaMemcpyHostToDevice, h->stream));
-        h->has_na = true; // assume so; nobs is counted lazily by the caller if needed
-        h->nobs = -1;
+        unsigned long long *cnt = (unsigned long long *)h->scal + SC_TMP;
+        CK(cudaMemsetAsync(cnt, 0, 8, h->stream));
+        popcount_kernel<<<nblk(N * h->Fw, 256), 256, 0, h->stream>>>(h->mc, N * h->Fw, cnt);
+        LAUNCH_CHECK();
+        unsigned long long c = 0;
+        CK(cudaMemcpyAsync(&c, cnt, 8, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        h->nobs = (int64_t)c;
+        h->has_na = (h->nobs != F * N);
     } else {
         fill_mask_kernel<<<nblk(N * h->Fw, 256), 256, 0, h->stream>>>(h->mc, N, h->Fw, F);
         LAUNCH_CHECK();
@@ -561,16 +568,22 @@ extern "C" int nbmf_vb_step(nbmf_handle *h, int checklb)
     // Dirichlet-side statistic: owner = rows, reduce over the local columns, then
     // the one exchange step, then n_total = A (.) G_F
     if ((rc = run_pass(h, 1, checklb ? h->scal + SC_SUMLOGD : nullptr))) return rc;
+    if (checklb && use_tensor_path(h) && (rc = tp_log_correction(h, 1, h->scal + SC_SUMLOGD))) return rc;
     CK(cudaEventRecord(h->ev[3], h->stream));
     if ((rc = exchange(h, h->GF, (size_t)h->F * h->Kp))) return rc;
     CK(cudaEventRecord(h->ev[4], h->stream));
     // Beta-side statistics: owner = (column, branch) lanes, all local
     if ((rc = run_pass(h, 0, nullptr))) return rc;
-    finalize_stats_kernel<<<nblk(h->F * h->Kp, 256), 256, 0, h->stream>>>(h->A, h->GF, h->F * h->Kp, h->statF);
-    LAUNCH_CHECK();
-    finalize_stats_kernel<<<nblk(2 * h->N * h->Kp, 256), 256, 0, h->stream>>>(h->BB, h->GN, 2 * h->N * h->Kp, h->statN);
-    LAUNCH_CHECK();
-    h->timing.launches += 2;
+    if (checklb && use_tensor_path(h) && (rc = tp_log_correction(h, 0, h->scal + SC_SUMLOGD))) return rc;
+    if (use_tensor_path(h)) {
+        if ((rc = tp_finalize(h))) return rc;
+    } else {
+        finalize_stats_kernel<<<nblk(h->F * h->Kp, 256), 256, 0, h->stream>>>(h->A, h->GF, h->F * h->Kp, h->statF);
+        LAUNCH_CHECK();
+        finalize_stats_kernel<<<nblk(2 * h->N * h->Kp, 256), 256, 0, h->stream>>>(h->BB, h->GN, 2 * h->N * h->Kp, h->statN);
+        LAUNCH_CHECK();
+        h->timing.launches += 2;
+    }
     // lb_i = sum log D + (pW - qW) + (pH - qH).  The first and third are local to the
     // rank's columns, the second is replicated (nbmf_vb_get_lb_terms for sharded runs).
     CK(cudaMemcpyAsync(h->lbs + 3 * (size_t)i, h->scal + SC_SUMLOGD, 24, cudaMemcpyDeviceToDevice, h->stream));
@@ -597,10 +610,11 @@ extern "C" int nbmf_vb_end(nbmf_handle *h, double *E_W, double *E_H, double *low
         cudaEventElapsedTime(&ms, h->ev[3], h->ev[4]); h->timing.exchange_ms = ms;
         cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]); h->timing.pass_cols_ms = ms;
     }
+    int rc;
+    if (use_tensor_path(h) && (rc = tp_check_error(h))) return rc;
     double neg = 0;
     CK(cudaMemcpy(&neg, h->scal + SC_NEG, 8, cudaMemcpyDeviceToHost));
     if (neg != 0.0) return fail(h, NBMF_ERR_NEGATIVE, "Negative values in alpha_vb / beta_vb / gamma_vb");
-    int rc;
     const int K = h->vb_K;
     if (h->vb_iter == 0) { // E_W / E_H of the current statistics
         if ((rc = run_params(h, K, h->vb_alpha, h->vb_beta, h->vb_gamma, h->vb_mean_params, 0))) return rc;
@@ -663,9 +677,15 @@ extern "C" int nbmf_lower_bound(nbmf_handle *h, int K, double alpha, double beta
     int rc;
     if ((rc = run_params(h, K, alpha, beta, gamma, 0, 1))) return rc;
     if ((rc = run_pass(h, 1, h->scal + SC_SUMLOGD))) return rc;
+    if (use_tensor_path(h)) {
+        if ((rc = tp_log_correction(h, 1, h->scal + SC_SUMLOGD))) return rc;
+        if ((rc = run_pass(h, 0, nullptr))) return rc;
+        if ((rc = tp_log_correction(h, 0, h->scal + SC_SUMLOGD))) return rc;
+    }
     double s[3];
     CK(cudaMemcpyAsync(s, h->scal, 24, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    if (use_tensor_path(h) && (rc = tp_check_error(h))) return rc;
     if (lb) *lb = s[0] + s[1] + s[2];
     if (terms7) { // pW-qW, pZ+pV-qZ (= sum log D), pH-qH, rest 0
         for (int i = 0; i < 7; i++) terms7[i] = 0;

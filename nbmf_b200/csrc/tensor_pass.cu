@@ -1,7 +1,859 @@
-// tensor_pass.cu -- placeholder until the tcgen05 kernel lands (same commit series)
+// tensor_pass.cu -- the tcgen05 / TMEM / TMA contraction pass of libnbmf_cuda.
+//
+// One kernel serves both statistics ("owner / stream" form, see kernels_basic.cuh):
+//   owner lane l (128 per CTA tile, = TMEM lane)  operand u_l   (f16 hi + lo, in TMEM)
+//   streamed row c (256 per step, via TMA)        operand w_c   (f16 hi, in smem)
+//   stage 1   S[l][c]  = u_l . w_c   (hi parts only)      tcgen05.mma TS, fp32 in TMEM
+//   epilogue  R[l][c]  = sel(l,c) / S[l][c]  -> f16, written back over S in TMEM
+//   stage 2   G[l][:] += sum_c R[l][c] (w_hi + w_lo)_c    2 x tcgen05.mma TS, B operand MN-major
+// rows pass: owner = row f (u = A_f), stream = (n,b) pairs (w = B_b(n,:)), sel = mask & (v==b)
+// cols pass: owner = (n,b) lane (u = B_b(n,:)), stream = row f (w = A_f), same sel.
+//
+// Precision (DESIGN.md "tensor path", measured with tools/tp_accuracy.py and a NumPy
+// emulation): S only feeds R = 1/S, whose relative error is an average over k of the
+// operands' f16 rounding errors and largely cancels against the numerator -- one f16 pass
+// is enough.  The numerator (stage 2) carries the streamed operand's rounding error
+// directly into the statistic, so there the operand is split hi+lo (22 bits).  R is a
+// single f16 (its error is independent per entry and averages over the reduction).  All
+// accumulation is fp32 in TMEM over a bounded chunk of steps; chunk partials are summed
+// in fp64, and each statistic row is rescaled to its exact observation count
+// (tp_finalize_kernel), which removes the round-toward-zero bias of the tensor pipe's
+// accumulator.
+//
+// Work decomposition: item = (stream chunk, owner tile); persistent CTAs take items
+// round-robin with the owner tile fastest, so the CTAs running at any time stream
+// the SAME chunk (served once from HBM, then from L2).
+//
+// Warp roles (384 threads): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM
+// allocator, warps 4-7 epilogue of column-half 0, warps 8-11 epilogue of half 1.
 #include "tensor_pass.h"
-bool tp_supported(const nbmf_handle *) { return false; }
-int tp_prepare(nbmf_handle *h) { h->err = "tensor path not built"; return NBMF_ERR_UNSUPPORTED; }
-int tp_convert_operands(nbmf_handle *h) { h->err = "tensor path not built"; return NBMF_ERR_UNSUPPORTED; }
-int tp_pass(nbmf_handle *h, int, double *) { h->err = "tensor path not built"; return NBMF_ERR_UNSUPPORTED; }
-void tp_free(nbmf_handle *) {}
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+
+#define TP_THREADS 384
+#define TP_SPIN_LIMIT (1u << 20)
+
+// ---------------------------------------------------------------------------
+// host-side state
+// ---------------------------------------------------------------------------
+struct TPState {
+    int KP = 0;
+    int64_t Fpad = 0, N2pad = 0;          // padded row counts of the f16 operand matrices
+    __half *A_hi = nullptr, *A_lo = nullptr;   // [Fpad][KP]
+    __half *B_hi = nullptr, *B_lo = nullptr;   // [N2pad][KP]
+    float *partial = nullptr; size_t partial_bytes = 0;
+    CUtensorMap tmA, tmB, tmAlo, tmBlo;
+    unsigned long long *dmax = nullptr;   // [0] max A bits, [1] max BB bits
+    int *dexp = nullptr;                  // [0] eA, [1] eB
+    double *dacc = nullptr;               // [0] sum log2 S, [1] clamp count
+    int *derr = nullptr;                  // kernel abort / error flag
+    double *cntF = nullptr, *cntN = nullptr; // exact observed counts per owner lane: [F], [2N]
+    bool counts_ready = false;
+    int chunk_steps = 32;
+};
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode()
+{
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)p;
+    }
+    return fn;
+}
+
+bool tp_supported(const nbmf_handle *h)
+{
+    if (h->cc_major != 10) return false;
+    if (h->Kc <= 32 || h->Kc > 128) return false;
+    if (h->F < 256 || h->N < 256) return false;
+    return true;
+}
+
+void tp_free(nbmf_handle *h)
+{
+    TPState *s = (TPState *)h->tp;
+    if (!s) return;
+    cudaFree(s->A_hi); cudaFree(s->A_lo); cudaFree(s->B_hi); cudaFree(s->B_lo);
+    cudaFree(s->partial); cudaFree(s->dmax); cudaFree(s->dexp); cudaFree(s->dacc); cudaFree(s->derr);
+    cudaFree(s->cntF); cudaFree(s->cntN);
+    delete s;
+    h->tp = nullptr;
+}
+
+static int make_map(nbmf_handle *h, CUtensorMap *tm, void *base, int64_t rows, int KP)
+{
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) { h->err = "cuTensorMapEncodeTiled entry point not available"; return NBMF_ERR_CUDA; }
+    cuuint64_t dims[2] = {(cuuint64_t)KP, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)KP * 2};
+    cuuint32_t box[2] = {64, 128};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { h->err = "cuTensorMapEncodeTiled failed"; return NBMF_ERR_CUDA; }
+    return NBMF_OK;
+}
+
+int tp_prepare(nbmf_handle *h)
+{
+    if (h->cc_major != 10) { h->err = "tensor path needs an sm_100 device"; return NBMF_ERR_UNSUPPORTED; }
+    if (h->Kc <= 32 || h->Kc > 128) { h->err = "tensor path supports 32 < K <= 128"; return NBMF_ERR_UNSUPPORTED; }
+    const int KP = h->Kc <= 64 ? 64 : 128;
+    if (KP != h->Kp) { h->err = "internal: tensor KP != fp64 Kp"; return NBMF_ERR_STATE; }
+    TPState *s = (TPState *)h->tp;
+    if (s && s->KP == KP) return NBMF_OK;
+    tp_free(h);
+    s = new TPState();
+    h->tp = s;
+    s->KP = KP;
+    s->Fpad = round_up64(h->F, 256);
+    s->N2pad = round_up64(2 * h->N, 256);
+    size_t ab = (size_t)s->Fpad * KP * 2, bb = (size_t)s->N2pad * KP * 2;
+    cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess) e = cudaMalloc(&s->A_hi, ab);
+    if (e == cudaSuccess) e = cudaMalloc(&s->A_lo, ab);
+    if (e == cudaSuccess) e = cudaMalloc(&s->B_hi, bb);
+    if (e == cudaSuccess) e = cudaMalloc(&s->B_lo, bb);
+    if (e == cudaSuccess) e = cudaMalloc(&s->dmax, 16);
+    if (e == cudaSuccess) e = cudaMalloc(&s->dexp, 8);
+    if (e == cudaSuccess) e = cudaMalloc(&s->dacc, 16);
+    if (e == cudaSuccess) e = cudaMalloc(&s->derr, 16);
+    if (e == cudaSuccess) e = cudaMalloc(&s->cntF, (size_t)h->F * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&s->cntN, (size_t)2 * h->N * 8);
+    if (e != cudaSuccess) { cudaGetLastError(); tp_free(h); h->err = "tensor path allocation failed"; return NBMF_ERR_OOM; }
+    cudaMemsetAsync(s->A_hi, 0, ab, h->stream); cudaMemsetAsync(s->A_lo, 0, ab, h->stream);
+    cudaMemsetAsync(s->B_hi, 0, bb, h->stream); cudaMemsetAsync(s->B_lo, 0, bb, h->stream);
+    cudaMemsetAsync(s->derr, 0, 16, h->stream);
+    int rc = make_map(h, &s->tmA, s->A_hi, s->Fpad, KP);
+    if (rc) return rc;
+    rc = make_map(h, &s->tmB, s->B_hi, s->N2pad, KP);
+    if (rc) return rc;
+    rc = make_map(h, &s->tmAlo, s->A_lo, s->Fpad, KP);
+    if (rc) return rc;
+    rc = make_map(h, &s->tmBlo, s->B_lo, s->N2pad, KP);
+    if (rc) return rc;
+    s->chunk_steps = h->opts.flush_interval > 0 ? h->opts.flush_interval : 64;
+    const char *env = getenv("NBMF_TP_CHUNK_STEPS");
+    if (env && atoi(env) > 0) s->chunk_steps = atoi(env);
+    return NBMF_OK;
+}
+
+// ---------------------------------------------------------------------------
+// operand conversion: fp64 -> power-of-two scaled f16 hi + lo
+// ---------------------------------------------------------------------------
+__global__ void tp_max_kernel(const double *__restrict__ x, int64_t count, unsigned long long *out)
+{
+    __shared__ unsigned long long sh[32];
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double m = 0.0;
+    for (; i < count; i += (int64_t)gridDim.x * blockDim.x) m = fmax(m, x[i]);
+    unsigned long long b = (unsigned long long)__double_as_longlong(m);
+    for (int o = 16; o > 0; o >>= 1) b = max(b, __shfl_xor_sync(0xffffffffu, b, o));
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = b;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        b = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0ull;
+        for (int o = 16; o > 0; o >>= 1) b = max(b, __shfl_xor_sync(0xffffffffu, b, o));
+        if (threadIdx.x == 0) atomicMax(out, b);
+    }
+}
+
+// exponent e with max * 2^e in [2^14, 2^15)
+__global__ void tp_exp_kernel(const unsigned long long *dmax, int *dexp)
+{
+    int i = threadIdx.x;
+    if (i < 2) {
+        double m = __longlong_as_double((long long)dmax[i]);
+        int x = 0;
+        if (m > 0.0) frexp(m, &x); // m = f * 2^x, f in [0.5, 1)
+        dexp[i] = 15 - x;
+    }
+}
+
+__global__ void tp_split_kernel(const double *__restrict__ x, int64_t count, const int *dexp, int which,
+                                __half *__restrict__ hi, __half *__restrict__ lo)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    double v = ldexp(x[i], dexp[which]);
+    __half h = __double2half(v);
+    hi[i] = h;
+    lo[i] = __double2half(v - (double)__half2float(h));
+}
+
+// exact per-lane observation counts: sum_k of each statistic row is an integer known
+// from the data (sum_k E_Z(f,k,n) = 1 for every observed entry, collapsed_gibbs_z_VB.cpp:457)
+__global__ void tp_count_rows_kernel(const uint32_t *__restrict__ mr, int64_t F, int64_t Nw, double *cntF)
+{
+    int64_t f = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (f >= F) return;
+    unsigned c = 0;
+    for (int64_t w = lane; w < Nw; w += 32) c += __popc(mr[f * Nw + w]);
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) cntF[f] = (double)c;
+}
+__global__ void tp_count_cols_kernel(const uint32_t *__restrict__ vc, const uint32_t *__restrict__ mc, int64_t N,
+                                     int64_t Fw, double *cntN)
+{
+    int64_t n = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (n >= N) return;
+    unsigned c1 = 0, c0 = 0;
+    for (int64_t w = lane; w < Fw; w += 32) {
+        uint32_t v = vc[n * Fw + w], m = mc[n * Fw + w];
+        c1 += __popc(v & m); c0 += __popc(~v & m);
+    }
+    for (int o = 16; o > 0; o >>= 1) { c1 += __shfl_xor_sync(0xffffffffu, c1, o); c0 += __shfl_xor_sync(0xffffffffu, c0, o); }
+    if (lane == 0) { cntN[2 * n + 1] = (double)c1; cntN[2 * n] = (double)c0; }
+}
+
+// stat = U (.) G, then each lane's row is rescaled so that its sum over k equals the exact
+// observation count of that lane.  This projects out every per-lane multiplicative error of
+// the low-precision contraction (fp32 accumulation in the tensor pipe rounds toward zero).
+__global__ void tp_finalize_kernel(const double *__restrict__ U, const double *__restrict__ G,
+                                   const double *__restrict__ cnt, int64_t L, int Kp, double *__restrict__ stat)
+{
+    int64_t l = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (l >= L) return;
+    double v[4], s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        int k = lane + 32 * i;
+        v[i] = (k < Kp) ? U[l * Kp + k] * G[l * Kp + k] : 0.0;
+        s += v[i];
+    }
+    s = warp_sum(s);
+    const double sc = (s > 0.0) ? cnt[l] / s : 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        int k = lane + 32 * i;
+        if (k < Kp) stat[l * Kp + k] = v[i] * sc;
+    }
+}
+
+// First-order ELBO correction for the single-f16 stage 1:
+//   sum log D  ~=  sum log D_hi + sum_lk (U - U_hi)_lk G_lk     over both passes' owners,
+// because D - D_hi = (U-U_hi).W_hi + U_hi.(W-W_hi) + O(2^-24) and sum_c R_lc W_c = G_l.
+__global__ void tp_logcorr_kernel(const double *__restrict__ U, const __half *__restrict__ Uhi, const double *__restrict__ G,
+                                  int64_t count, const int *dexp, int which, double *sumlogD)
+{
+    __shared__ double sh[32];
+    const double inv = ldexp(1.0, -dexp[which]);
+    double t = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
+        t += (U[i] - (double)__half2float(Uhi[i]) * inv) * G[i];
+    t = block_sum(t, sh);
+    if (threadIdx.x == 0) atomicAdd(sumlogD, t);
+}
+
+int tp_log_correction(nbmf_handle *h, int owner_rows, double *sumlogD)
+{
+    TPState *s = (TPState *)h->tp;
+    if (!s || !sumlogD) return NBMF_OK;
+    const int64_t cnt = (owner_rows ? h->F : 2 * h->N) * (int64_t)s->KP;
+    tp_logcorr_kernel<<<(unsigned)std::min<int64_t>(2048, (cnt + 255) / 256), 256, 0, h->stream>>>(
+        owner_rows ? h->A : h->BB, owner_rows ? s->A_hi : s->B_hi, owner_rows ? h->GF : h->GN, cnt, s->dexp,
+        owner_rows ? 0 : 1, sumlogD);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { h->err = std::string("tp_log_correction: ") + cudaGetErrorString(e); return NBMF_ERR_CUDA; }
+    h->timing.launches += 1;
+    return NBMF_OK;
+}
+
+int tp_finalize(nbmf_handle *h)
+{
+    TPState *s = (TPState *)h->tp;
+    if (!s) { h->err = "tp_finalize before tp_prepare"; return NBMF_ERR_STATE; }
+    if (!s->counts_ready) {
+        tp_count_rows_kernel<<<(unsigned)((h->F * 32 + 255) / 256), 256, 0, h->stream>>>(h->mr, h->F, h->Nw, s->cntF);
+        tp_count_cols_kernel<<<(unsigned)((h->N * 32 + 255) / 256), 256, 0, h->stream>>>(h->vc, h->mc, h->N, h->Fw, s->cntN);
+        if (h->hook) { // row counts are over ALL columns: sum the ranks' local counts once
+            int rc = h->hook(h->hook_ctx, (void *)s->cntF, (size_t)h->F, (void *)h->stream);
+            if (rc) { h->err = "allreduce hook failed"; return NBMF_ERR_STATE; }
+        }
+        s->counts_ready = true;
+    }
+    tp_finalize_kernel<<<(unsigned)((h->F * 32 + 255) / 256), 256, 0, h->stream>>>(h->A, h->GF, s->cntF, h->F, s->KP, h->statF);
+    tp_finalize_kernel<<<(unsigned)((2 * h->N * 32 + 255) / 256), 256, 0, h->stream>>>(h->BB, h->GN, s->cntN, 2 * h->N, s->KP, h->statN);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { h->err = std::string("tp_finalize: ") + cudaGetErrorString(e); return NBMF_ERR_CUDA; }
+    h->timing.launches += 2;
+    return NBMF_OK;
+}
+
+int tp_convert_operands(nbmf_handle *h)
+{
+    TPState *s = (TPState *)h->tp;
+    if (!s) { h->err = "tp_convert_operands before tp_prepare"; return NBMF_ERR_STATE; }
+    const int64_t ca = h->F * (int64_t)s->KP, cb = 2 * h->N * (int64_t)s->KP;
+    cudaMemsetAsync(s->dmax, 0, 16, h->stream);
+    tp_max_kernel<<<(unsigned)std::min<int64_t>(1024, (ca + 255) / 256), 256, 0, h->stream>>>(h->A, ca, s->dmax);
+    tp_max_kernel<<<(unsigned)std::min<int64_t>(1024, (cb + 255) / 256), 256, 0, h->stream>>>(h->BB, cb, s->dmax + 1);
+    tp_exp_kernel<<<1, 32, 0, h->stream>>>(s->dmax, s->dexp);
+    tp_split_kernel<<<(unsigned)((ca + 255) / 256), 256, 0, h->stream>>>(h->A, ca, s->dexp, 0, s->A_hi, s->A_lo);
+    tp_split_kernel<<<(unsigned)((cb + 255) / 256), 256, 0, h->stream>>>(h->BB, cb, s->dexp, 1, s->B_hi, s->B_lo);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { h->err = std::string("tp_convert_operands: ") + cudaGetErrorString(e); return NBMF_ERR_CUDA; }
+    h->timing.launches += 5;
+    return NBMF_OK;
+}
+
+// ---------------------------------------------------------------------------
+// PTX helpers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"(bar), "r"(bytes)
+                 : "memory");
+}
+// bounded wait: on timeout raise the CTA-wide abort flag so that the kernel drains
+// instead of hanging the GPU; the host reports the error.
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, volatile int *abort_flag, int code)
+{
+    uint32_t ok = 0;
+    for (uint32_t spin = 0; spin < TP_SPIN_LIMIT; spin++) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok)
+                     : "r"(bar), "r"(parity)
+                     : "memory");
+        if (ok) return true;
+        if ((spin & 1023u) == 1023u && *abort_flag) return false;
+    }
+    *abort_flag = code;
+    return false;
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *tm, int c0, int c1, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem desc]
+__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc)
+{
+    asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
+                 " tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n}"
+                 ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc), "r"(0u)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&r)[16])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+                 "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+                 "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+                 : "memory");
+}
+__device__ __forceinline__ float fast_rcp(float x)
+{
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float fast_lg2(float x)
+{
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi)
+{
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+
+// smem matrix descriptor, SWIZZLE_128B (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout_type=2 [61,64))
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32=1 [4,6), a/b format F16=0,
+// a_major [15], b_major [16] (0 = K, 1 = MN), N>>3 [17,23), M>>4 [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int b_mn_major)
+{
+    return (1u << 4) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------
+struct TPArgs {
+    const __half *U_hi;            // owner operand rows [Lpad][KP] (hi part only)
+    const uint32_t *vbits, *mbits; // [owner_rows][words] packed along the streamed index
+    int64_t words;
+    int64_t L;                     // owner lanes
+    int64_t owner_tiles;           // ceil(L/128)
+    int64_t stream_steps;          // total steps of 128 streamed rows
+    int chunk_steps, n_chunks;
+    float *partial;                // [n_chunks][owner_tiles*128][KP]
+    const int *dexp;               // eA, eB
+    double *dacc;                  // [0] += sum log2 S over selected entries (rows pass only)
+    int *derr;
+    int want_log;
+    float *dbg;                    // optional debug dump
+};
+
+// One step = 128 streamed rows.  Shared-memory stage: [hi: KB blocks][lo: KB blocks], each
+// block = 128 rows x 128 B (64 f16 of k), SWIZZLE_128B, written by TMA.
+// TMEM columns: G [0,KP) | S^0 [KP,KP+128) | S^1 [KP+128,KP+256) | U [KP+256, KP+256+KP/2).
+// S^g holds the stage-1 accumulators of steps t = g (mod 2); R (f16) is written back over
+// the first 64 columns of S^g.
+template <int KP>
+struct TPCfg {
+    static constexpr int KB = KP / 64;
+    static constexpr int BLOCK_BYTES = 128 * 128;
+    static constexpr int PART_BYTES = KB * BLOCK_BYTES;     // hi (or lo) part of a stage
+    static constexpr int TILE_BYTES = 2 * PART_BYTES;
+    static constexpr int STAGES = (KP == 128) ? 3 : 6;
+    static constexpr int COL_G = 0;
+    static constexpr int COL_S0 = KP;
+    static constexpr int COL_S1 = KP + 128;
+    static constexpr int COL_U = KP + 256;
+    static constexpr int SMEM_BYTES = STAGES * TILE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int KP, bool ROWS>
+__global__ void __launch_bounds__(TP_THREADS, 1)
+tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__ CUtensorMap tmLo, TPArgs a)
+{
+    using C = TPCfg<KP>;
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + C::STAGES * C::TILE_BYTES;
+    auto BAR_FULL = [&](int s) { return bar_base + 8u * s; };
+    auto BAR_EMPTY = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
+    const uint32_t BAR_SFULL = bar_base + 8u * (2 * C::STAGES);      // [2]
+    const uint32_t BAR_RREADY = BAR_SFULL + 16;                        // [2]
+    const uint32_t BAR_GFULL = BAR_RREADY + 16;
+    const uint32_t BAR_UREADY = BAR_GFULL + 8;
+    __shared__ uint32_t tmem_base_sh;
+    __shared__ int abort_sh;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    volatile int *abort_flag = &abort_sh;
+
+    if (threadIdx.x == 0) {
+        abort_sh = 0;
+        for (int s = 0; s < C::STAGES; s++) { mbar_init(BAR_FULL(s), 1); mbar_init(BAR_EMPTY(s), 1); }
+        mbar_init(BAR_SFULL, 1); mbar_init(BAR_SFULL + 8, 1);
+        mbar_init(BAR_RREADY, 128); mbar_init(BAR_RREADY + 8, 128);
+        mbar_init(BAR_GFULL, 1);
+        mbar_init(BAR_UREADY, 256);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_sh)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_sh;
+
+    const int64_t n_items = (int64_t)a.n_chunks * a.owner_tiles;
+    const int eU = ROWS ? a.dexp[0] : a.dexp[1];
+    const int eW = ROWS ? a.dexp[1] : a.dexp[0];
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int64_t w = blockIdx.x; w < n_items; w += gridDim.x) {
+                const int chunk = (int)(w / a.owner_tiles);
+                const int64_t t0 = (int64_t)chunk * a.chunk_steps;
+                const int nst = (int)min((int64_t)a.chunk_steps, a.stream_steps - t0);
+                for (int t = 0; t < nst; t++) {
+                    if (!mbar_wait(BAR_EMPTY(stage), phase ^ 1, abort_flag, 1)) break;
+                    mbar_expect_tx(BAR_FULL(stage), C::TILE_BYTES);
+                    const uint32_t dst = smem_base + stage * C::TILE_BYTES;
+                    const int row0 = (int)((t0 + t) * 128);
+#pragma unroll
+                    for (int kb = 0; kb < C::KB; kb++) {
+                        tma_load_2d(dst + kb * C::BLOCK_BYTES, &tmHi, kb * 64, row0, BAR_FULL(stage));
+                        tma_load_2d(dst + C::PART_BYTES + kb * C::BLOCK_BYTES, &tmLo, kb * 64, row0, BAR_FULL(stage));
+                    }
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+                if (*abort_flag) break;
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t IDESC1 = make_idesc(128, 128, 0);
+            constexpr uint32_t IDESC2 = make_idesc(128, KP, 1);
+            uint32_t stage = 0, phase = 0;      // smem ring (consumer side)
+            uint32_t rr_phase[2] = {0, 0};
+            uint32_t u_phase = 0;
+            // stage 1: S^g = U_hi . W_hi^T   (single pass; see DESIGN.md for why no lo term)
+            auto issue_stage1 = [&](uint32_t sbase, int g) {
+                const uint32_t d = tmem + (g ? C::COL_S1 : C::COL_S0);
+#pragma unroll
+                for (int kk = 0; kk < KP / 16; kk++) {
+                    const uint32_t baddr = sbase + (kk >> 2) * C::BLOCK_BYTES + (kk & 3) * 32;
+                    tc_mma_ts(d, tmem + C::COL_U + kk * 8, make_desc(baddr, 16, 1024), IDESC1, kk ? 1u : 0u);
+                }
+            };
+            // stage 2: G += R^g . (W_hi + W_lo)   (B operand MN-major: N = k contiguous)
+            auto issue_stage2 = [&](uint32_t sbase, int g, bool first) {
+                const uint32_t rcol = tmem + (g ? C::COL_S1 : C::COL_S0);
+#pragma unroll
+                for (int p = 0; p < 2; p++) {
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const uint32_t baddr = sbase + p * C::PART_BYTES + j * (16 * 128);
+                        tc_mma_ts(tmem + C::COL_G, rcol + j * 8, make_desc(baddr, C::BLOCK_BYTES, 1024), IDESC2,
+                                  (first && p == 0 && j == 0) ? 0u : 1u);
+                    }
+                }
+            };
+            uint32_t sb_ring[3]; uint32_t st_ring[3];   // tiles t, t+1, t+2 (indexed t % 3)
+            for (int64_t w = blockIdx.x; w < n_items; w += gridDim.x) {
+                const int chunk = (int)(w / a.owner_tiles);
+                const int64_t t0 = (int64_t)chunk * a.chunk_steps;
+                const int nst = (int)min((int64_t)a.chunk_steps, a.stream_steps - t0);
+                bool ok = mbar_wait(BAR_UREADY, u_phase, abort_flag, 2);
+                u_phase ^= 1;
+                tc_fence_after();
+                auto acquire = [&](int t) {   // wait for tile t, remember its stage, issue S(t)
+                    ok = ok && mbar_wait(BAR_FULL(stage), phase, abort_flag, 3);
+                    tc_fence_after();
+                    sb_ring[t % 3] = smem_base + stage * C::TILE_BYTES;
+                    st_ring[t % 3] = stage;
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                    issue_stage1(sb_ring[t % 3], t & 1);
+                    tc_commit(BAR_SFULL + 8u * (t & 1));
+                };
+                acquire(0);
+                if (nst > 1) acquire(1);
+                for (int t = 0; t < nst && ok; t++) {
+                    const int g = t & 1;
+                    ok = ok && mbar_wait(BAR_RREADY + 8u * g, rr_phase[g], abort_flag, 4);
+                    rr_phase[g] ^= 1;
+                    tc_fence_after();
+                    issue_stage2(sb_ring[t % 3], g, t == 0);
+                    tc_commit(BAR_EMPTY(st_ring[t % 3]));   // tile t fully consumed
+                    if (t + 2 < nst) acquire(t + 2);
+                }
+                tc_commit(BAR_GFULL);
+                if (!ok) break;
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int grp = (warp - 4) >> 2;            // handles steps t = grp (mod 2)
+        const int q = warp & 3;                     // TMEM lane quarter
+        const int lrow = q * 32 + lane;             // owner lane within the tile
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        const uint32_t t_s = tmem + lane_addr + (grp ? C::COL_S1 : C::COL_S0);
+        const uint32_t bar_sfull = BAR_SFULL + 8u * grp, bar_rready = BAR_RREADY + 8u * grp;
+        uint32_t sf_phase = 0, g_phase = 0;
+        const float c0 = exp2f((float)(eU + eW - 14));
+        double log_acc_total = 0.0;
+        bool first_item = true, ok = true;
+        int64_t prev_w = -1;
+        auto drain_G = [&](int64_t pw) {
+            const int pchunk = (int)(pw / a.owner_tiles);
+            const int64_t ptile = pw % a.owner_tiles;
+            float *dst = a.partial + (((int64_t)pchunk * a.owner_tiles + ptile) * 128 + lrow) * KP + grp * (KP / 2);
+#pragma unroll
+            for (int cc = 0; cc < KP / 64; cc++) {
+                uint32_t r[32];
+                tc_ld32(tmem + lane_addr + C::COL_G + grp * (KP / 2) + cc * 32, r);
+                tc_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 32; i += 4)
+                    *reinterpret_cast<uint4 *>(dst + cc * 32 + i) = make_uint4(r[i], r[i + 1], r[i + 2], r[i + 3]);
+            }
+        };
+        for (int64_t w = blockIdx.x; w < n_items && ok; w += gridDim.x) {
+            const int chunk = (int)(w / a.owner_tiles);
+            const int64_t tile = w % a.owner_tiles;
+            const int64_t t0 = (int64_t)chunk * a.chunk_steps;
+            const int nst = (int)min((int64_t)a.chunk_steps, a.stream_steps - t0);
+            const int64_t l = tile * 128 + lrow;
+            const bool lane_ok = l < a.L;
+            // ---- drain G of the previous item
+            if (!first_item) {
+                ok = ok && mbar_wait(BAR_GFULL, g_phase, abort_flag, 7);
+                g_phase ^= 1;
+                tc_fence_after();
+                drain_G(prev_w);
+            }
+            // ---- owner operand of this item -> TMEM (each group writes half of the k range)
+            {
+                const __half *src = a.U_hi + l * KP + grp * (KP / 2);
+                const uint32_t ucol = tmem + lane_addr + C::COL_U + grp * (KP / 4);
+#pragma unroll
+                for (int cc = 0; cc < KP / 64; cc++) {
+                    uint32_t r[16];
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        uint4 v = lane_ok ? __ldg(reinterpret_cast<const uint4 *>(src + cc * 32) + i) : make_uint4(0, 0, 0, 0);
+                        r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
+                    }
+                    tc_st16(ucol + cc * 16, r);
+                }
+                tc_wait_st();
+                tc_fence_before();
+                mbar_arrive(BAR_UREADY);
+            }
+            first_item = false;
+            prev_w = w;
+            // ---- steps t = grp, grp+2, ...
+            float log_acc = 0.f;
+            const int64_t orow = ROWS ? l : (l >> 1);
+            const uint32_t bsel = ROWS ? 0u : (uint32_t)(l & 1);
+            const uint32_t *vrow = a.vbits + orow * a.words;
+            const uint32_t *mrow = a.mbits + orow * a.words;
+            // words per step: ROWS: 64 n -> 2 words; COLS: 128 f -> 4 words
+            constexpr int WPS = ROWS ? 2 : 4;
+            uint32_t bv[WPS], bm[WPS];
+            auto load_bits = [&](int t) {
+                const int64_t wi = (t0 + t) * WPS;
+#pragma unroll
+                for (int i = 0; i < WPS; i++) {
+                    bv[i] = lane_ok ? __ldg(vrow + wi + i) : 0u;
+                    bm[i] = lane_ok ? __ldg(mrow + wi + i) : 0u;
+                }
+            };
+            if (grp < nst) load_bits(grp);
+            for (int t = grp; t < nst && ok; t += 2) {
+                uint32_t sel[WPS], vv[WPS];
+#pragma unroll
+                for (int i = 0; i < WPS; i++) {
+                    vv[i] = bv[i];
+                    sel[i] = ROWS ? bm[i] : ((bsel ? bv[i] : ~bv[i]) & bm[i]);
+                }
+                if (t + 2 < nst) load_bits(t + 2);
+                ok = ok && mbar_wait(bar_sfull, sf_phase, abort_flag, 8);
+                sf_phase ^= 1;
+                tc_fence_after();
+#pragma unroll
+                for (int cc = 0; cc < 4; cc++) {
+                    uint32_t s[32], rp[16];
+                    tc_ld32(t_s + cc * 32, s);
+                    tc_wait_ld();
+                    if (a.dbg && w == 0 && t < 2) {
+#pragma unroll
+                        for (int i = 0; i < 32; i++) a.dbg[(lrow * 256) + t * 128 + cc * 32 + i] = __uint_as_float(s[i]);
+                    }
+                    if (ROWS) {
+                        // 32 columns = 16 entries (n) x 2 branches, column 2j+b
+                        const uint32_t m16 = (sel[cc >> 1] >> ((cc & 1) * 16)) & 0xffffu;
+                        const uint32_t v16 = (vv[cc >> 1] >> ((cc & 1) * 16)) & 0xffffu;
+#pragma unroll
+                        for (int j = 0; j < 16; j++) {
+                            const bool vb = (v16 >> j) & 1u, mb = (m16 >> j) & 1u;
+                            const float sv = __uint_as_float(vb ? s[2 * j + 1] : s[2 * j]);
+                            float r = fminf(c0 * fast_rcp(sv), 65504.f);
+                            r = mb ? r : 0.f;
+                            if (a.want_log) log_acc += mb ? fast_lg2(sv) : 0.f;
+                            rp[j] = pack_h2(vb ? 0.f : r, vb ? r : 0.f);
+                        }
+                    } else {
+                        const uint32_t m32 = sel[cc];
+#pragma unroll
+                        for (int j = 0; j < 16; j++) {
+                            const float s0 = __uint_as_float(s[2 * j]), s1 = __uint_as_float(s[2 * j + 1]);
+                            const float r0 = ((m32 >> (2 * j)) & 1u) ? fminf(c0 * fast_rcp(s0), 65504.f) : 0.f;
+                            const float r1 = ((m32 >> (2 * j + 1)) & 1u) ? fminf(c0 * fast_rcp(s1), 65504.f) : 0.f;
+                            rp[j] = pack_h2(r0, r1);
+                        }
+                    }
+                    tc_st16(t_s + cc * 16, rp);
+                }
+                tc_wait_st();
+                tc_fence_before();
+                mbar_arrive(bar_rready);
+            }
+            log_acc_total += (double)log_acc;
+        }
+        // ---- drain G of the last item
+        if (!first_item && ok) {
+            ok = mbar_wait(BAR_GFULL, g_phase, abort_flag, 9);
+            tc_fence_after();
+            drain_G(prev_w);
+        }
+        if (a.want_log) {
+            double v = warp_sum(log_acc_total);
+            if (lane == 0) atomicAdd(&a.dacc[0], v);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0 && abort_sh) atomicMax(a.derr, abort_sh);
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+    }
+}
+
+// partial sums (fp32, per chunk) -> G (fp64), un-scaled:  G = sum_chunks partial * 2^(14 - eW)
+__global__ void tp_reduce_kernel(const float *__restrict__ partial, int n_chunks, int64_t Lpad, int64_t L, int KP,
+                                 const int *dexp, int which_w, double *__restrict__ G)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= L * KP) return;
+    double s = 0.0;
+    for (int c = 0; c < n_chunks; c++) s += (double)partial[(int64_t)c * Lpad * KP + i];
+    G[i] = ldexp(s, 14 - dexp[which_w]);
+}
+
+// sumlogD += ln2 * (sum log2 S - nsel * (eA + eB))
+__global__ void tp_logfix_kernel(const double *dacc, const int *dexp, double nsel, double *sumlogD)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0)
+        *sumlogD += 0.6931471805599453 * (dacc[0] - nsel * (double)(dexp[0] + dexp[1]));
+}
+
+template <int KP, bool ROWS>
+static cudaError_t launch_tp(const CUtensorMap &tm, const CUtensorMap &tmlo, const TPArgs &a, int grid, cudaStream_t st)
+{
+    cudaError_t e = cudaFuncSetAttribute(tp_pass_kernel<KP, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         TPCfg<KP>::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    tp_pass_kernel<KP, ROWS><<<grid, TP_THREADS, TPCfg<KP>::SMEM_BYTES, st>>>(tm, tmlo, a);
+    return cudaGetLastError();
+}
+
+static float *g_tp_dbg = nullptr; // set by nbmf_debug_tp_dump only
+
+int tp_pass(nbmf_handle *h, int owner_rows, double *sumlogD)
+{
+    TPState *s = (TPState *)h->tp;
+    if (!s) { h->err = "tp_pass before tp_prepare"; return NBMF_ERR_STATE; }
+    const int KP = s->KP;
+    TPArgs a{};
+    int64_t S_rows;
+    if (owner_rows) {
+        a.U_hi = s->A_hi; a.vbits = h->vr; a.mbits = h->mr; a.words = h->Nw;
+        a.L = h->F; S_rows = 2 * h->N;
+    } else {
+        a.U_hi = s->B_hi; a.vbits = h->vc; a.mbits = h->mc; a.words = h->Fw;
+        a.L = 2 * h->N; S_rows = h->F;
+    }
+    a.owner_tiles = (a.L + 127) / 128;
+    a.stream_steps = (S_rows + 127) / 128;
+    a.chunk_steps = (int)std::min<int64_t>(s->chunk_steps, a.stream_steps);
+    a.n_chunks = (int)((a.stream_steps + a.chunk_steps - 1) / a.chunk_steps);
+    const int64_t Lpad = a.owner_tiles * 128;
+    size_t need = (size_t)a.n_chunks * Lpad * KP * 4;
+    if (need > s->partial_bytes) {
+        cudaFree(s->partial); s->partial = nullptr; s->partial_bytes = 0;
+        if (cudaMalloc(&s->partial, need) != cudaSuccess) {
+            cudaGetLastError();
+            h->err = "tensor path: partial buffer allocation failed";
+            return NBMF_ERR_OOM;
+        }
+        s->partial_bytes = need;
+    }
+    a.partial = s->partial;
+    a.dexp = s->dexp; a.dacc = s->dacc; a.derr = s->derr;
+    a.want_log = (sumlogD != nullptr);
+    a.dbg = g_tp_dbg;
+    if (a.want_log) cudaMemsetAsync(s->dacc, 0, 16, h->stream);
+    const int64_t items = (int64_t)a.n_chunks * a.owner_tiles;
+    const int grid = (int)std::min<int64_t>(items, h->sm_count);
+    cudaError_t e;
+    if (KP == 128) e = owner_rows ? launch_tp<128, true>(s->tmB, s->tmBlo, a, grid, h->stream) : launch_tp<128, false>(s->tmA, s->tmAlo, a, grid, h->stream);
+    else e = owner_rows ? launch_tp<64, true>(s->tmB, s->tmBlo, a, grid, h->stream) : launch_tp<64, false>(s->tmA, s->tmAlo, a, grid, h->stream);
+    if (e != cudaSuccess) { h->err = std::string("tp_pass launch: ") + cudaGetErrorString(e); return NBMF_ERR_CUDA; }
+    tp_reduce_kernel<<<(unsigned)((a.L * KP + 255) / 256), 256, 0, h->stream>>>(s->partial, a.n_chunks, Lpad, a.L, KP, s->dexp,
+                                                                              owner_rows ? 1 : 0, owner_rows ? h->GF : h->GN);
+    if (a.want_log) tp_logfix_kernel<<<1, 32, 0, h->stream>>>(s->dacc, s->dexp, (double)h->nobs, sumlogD);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { h->err = std::string("tp_pass reduce: ") + cudaGetErrorString(e); return NBMF_ERR_CUDA; }
+    h->timing.launches += 2 + (a.want_log ? 1 : 0);
+    return NBMF_OK;
+}
+
+int tp_check_error(nbmf_handle *h)
+{
+    TPState *s = (TPState *)h->tp;
+    if (!s) return NBMF_OK;
+    int code = 0;
+    if (cudaMemcpy(&code, s->derr, 4, cudaMemcpyDeviceToHost) != cudaSuccess) { h->err = "tp_check_error: memcpy failed"; return NBMF_ERR_CUDA; }
+    if (code) {
+        char buf[96];
+        snprintf(buf, sizeof buf, "tensor kernel aborted on a barrier timeout (code %d)", code);
+        h->err = buf;
+        cudaMemset(s->derr, 0, 4);
+        return NBMF_ERR_CUDA;
+    }
+    return NBMF_OK;
+}
+
+// Debug aid (not part of the public header): runs params + one pass and returns the raw
+// stage-1 accumulators S (128 owner lanes x 256 streamed rows, fp32) of the first work
+// item's first step, plus the operand exponents.
+extern "C" int nbmf_debug_tp_dump(nbmf_handle *h, int owner_rows, float *S_out, int *exps_out)
+{
+    TPState *s = (TPState *)h->tp;
+    if (!s) { h->err = "no tensor state (call nbmf_vb_begin with a tensor precision first)"; return NBMF_ERR_STATE; }
+    float *d = nullptr;
+    if (cudaMalloc(&d, 128 * 256 * 4) != cudaSuccess) return NBMF_ERR_OOM;
+    cudaMemsetAsync(d, 0, 128 * 256 * 4, h->stream);
+    g_tp_dbg = d;
+    int rc = tp_pass(h, owner_rows, nullptr);
+    g_tp_dbg = nullptr;
+    cudaStreamSynchronize(h->stream);
+    if (rc == NBMF_OK) rc = tp_check_error(h);
+    cudaMemcpy(S_out, d, 128 * 256 * 4, cudaMemcpyDeviceToHost);
+    if (exps_out) cudaMemcpy(exps_out, s->dexp, 8, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    return rc;
+}
