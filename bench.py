@@ -30,6 +30,8 @@ WORKLOADS = {
                desc="VB_aspect contraction, synthetic DirBer 262144x262144, K=128 (BASELINE configs[4])"),
     "c4": dict(F=65536, N=65536, K=64, Kt=8, gamma=1.0, a=1.0, b=1.0, seed=4,
                desc="VB_aspect, synthetic DirBer 65536x65536, K=64 (BASELINE configs[3])"),
+    "big": dict(F=65536, N=65536, K=128, Kt=8, gamma=1.0 / 128, a=1.0, b=1.0, seed=7,
+                desc="VB_aspect, synthetic DirBer 65536x65536, K=128"),
     "mid": dict(F=16384, N=16384, K=128, Kt=8, gamma=1.0 / 128, a=1.0, b=1.0, seed=6,
                 desc="VB_aspect, synthetic DirBer 16384x16384, K=128"),
     "c1": dict(F=200, N=300, K=3, Kt=3, gamma=1.0, a=0.1, b=0.1, seed=1,

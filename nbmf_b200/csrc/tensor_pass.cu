@@ -98,7 +98,7 @@ static int make_map(nbmf_handle *h, CUtensorMap *tm, void *base, int64_t rows, i
     if (!enc) { h->err = "cuTensorMapEncodeTiled entry point not available"; return NBMF_ERR_CUDA; }
     cuuint64_t dims[2] = {(cuuint64_t)KP, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)KP * 2};
-    cuuint32_t box[2] = {64, 128};
+    cuuint32_t box[2] = {64, 64};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -145,7 +145,7 @@ int tp_prepare(nbmf_handle *h)
     if (rc) return rc;
     rc = make_map(h, &s->tmBlo, s->B_lo, s->N2pad, KP);
     if (rc) return rc;
-    s->chunk_steps = h->opts.flush_interval > 0 ? h->opts.flush_interval : 64;
+    s->chunk_steps = h->opts.flush_interval > 0 ? h->opts.flush_interval : 128;
     const char *env = getenv("NBMF_TP_CHUNK_STEPS");
     if (env && atoi(env) > 0) s->chunk_steps = atoi(env);
     return NBMF_OK;
@@ -353,6 +353,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *tm,
                  ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1)
                  : "memory");
 }
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n .reg .pred P;\n elect.sync _|P, 0xffffffff;\n selp.u32 %0, 1, 0, P;\n}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar)
@@ -365,6 +371,15 @@ __device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint
     asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
                  " tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n}"
                  ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc), "r"(0u)
+                 : "memory");
+}
+// same, descriptor given as {lo, hi} words
+__device__ __forceinline__ void tc_mma_ts2(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                           uint32_t acc)
+{
+    asm volatile("{\n .reg .pred p;\n .reg .b64 bd;\n setp.ne.b32 p, %5, 0;\n mov.b64 bd, {%2, %3};\n"
+                 " tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], bd, %4, {%6, %6, %6, %6}, p;\n}"
+                 ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc), "r"(0u)
                  : "memory");
 }
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32])
@@ -399,6 +414,12 @@ __device__ __forceinline__ float fast_lg2(float x)
     float y;
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+}
+__device__ __forceinline__ uint32_t pack_h2_sat(float lo, float hi) // +inf -> 65504
+{
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
 }
 __device__ __forceinline__ uint32_t pack_h2(float lo, float hi)
 {
@@ -436,7 +457,7 @@ struct TPArgs {
     int64_t words;
     int64_t L;                     // owner lanes
     int64_t owner_tiles;           // ceil(L/128)
-    int64_t stream_steps;          // total steps of 128 streamed rows
+    int64_t stream_steps;          // total steps of 64 streamed rows
     int chunk_steps, n_chunks;
     float *partial;                // [n_chunks][owner_tiles*128][KP]
     const int *dexp;               // eA, eB
@@ -444,28 +465,31 @@ struct TPArgs {
     int *derr;
     int want_log;
     float *dbg;                    // optional debug dump
+    int dbg_flags;                 // timing experiments only: 1 = skip lo TMA, 2 = skip all TMA
 };
 
-// One step = 128 streamed rows.  Shared-memory stage: [hi: KB blocks][lo: KB blocks], each
-// block = 128 rows x 128 B (64 f16 of k), SWIZZLE_128B, written by TMA.
-// TMEM columns: G [0,KP) | S^0 [KP,KP+128) | S^1 [KP+128,KP+256) | U [KP+256, KP+256+KP/2).
-// S^g holds the stage-1 accumulators of steps t = g (mod 2); R (f16) is written back over
-// the first 64 columns of S^g.
+// One step = 64 streamed rows.  Shared-memory stage: [hi: KB blocks][lo: KB blocks], each
+// block = 64 rows x 128 B (64 f16 of k), SWIZZLE_128B, written by TMA.  Seven stages (KP=128)
+// keep ~4 tiles in flight beyond the 3 that stage 1 / epilogue / stage 2 hold.
+// TMEM columns: G [0,KP) | 4 S slots of 64 columns [KP, KP+256) | U [KP+256, KP+256+KP/2).
+// Slot t&3 holds the stage-1 accumulators of step t; R (f16, 32 columns) is written back
+// over the slot.  Epilogue warpgroup g handles steps t = g (mod 2), i.e. slots g and g+2.
 template <int KP>
 struct TPCfg {
     static constexpr int KB = KP / 64;
-    static constexpr int BLOCK_BYTES = 128 * 128;
+    static constexpr int STEP_ROWS = 64;
+    static constexpr int BLOCK_BYTES = STEP_ROWS * 128;
     static constexpr int PART_BYTES = KB * BLOCK_BYTES;     // hi (or lo) part of a stage
     static constexpr int TILE_BYTES = 2 * PART_BYTES;
-    static constexpr int STAGES = (KP == 128) ? 3 : 6;
+    static constexpr int STAGES = (KP == 128) ? 7 : 12;
+    static constexpr int NSLOT = 4;
     static constexpr int COL_G = 0;
-    static constexpr int COL_S0 = KP;
-    static constexpr int COL_S1 = KP + 128;
+    static constexpr int COL_S = KP;                        // + 64 * slot
     static constexpr int COL_U = KP + 256;
-    static constexpr int SMEM_BYTES = STAGES * TILE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int SMEM_BYTES = STAGES * TILE_BYTES + 1024 /*align*/ + 512 /*barriers*/;
 };
 
-template <int KP, bool ROWS>
+template <int KP, bool ROWS, bool WANT_LOG>
 __global__ void __launch_bounds__(TP_THREADS, 1)
 tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__ CUtensorMap tmLo, TPArgs a)
 {
@@ -475,9 +499,9 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
     const uint32_t bar_base = smem_base + C::STAGES * C::TILE_BYTES;
     auto BAR_FULL = [&](int s) { return bar_base + 8u * s; };
     auto BAR_EMPTY = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
-    const uint32_t BAR_SFULL = bar_base + 8u * (2 * C::STAGES);      // [2]
-    const uint32_t BAR_RREADY = BAR_SFULL + 16;                        // [2]
-    const uint32_t BAR_GFULL = BAR_RREADY + 16;
+    const uint32_t BAR_SFULL = bar_base + 8u * (2 * C::STAGES);      // [4]
+    const uint32_t BAR_RREADY = BAR_SFULL + 8u * C::NSLOT;            // [4]
+    const uint32_t BAR_GFULL = BAR_RREADY + 8u * C::NSLOT;
     const uint32_t BAR_UREADY = BAR_GFULL + 8;
     __shared__ uint32_t tmem_base_sh;
     __shared__ int abort_sh;
@@ -488,8 +512,7 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
     if (threadIdx.x == 0) {
         abort_sh = 0;
         for (int s = 0; s < C::STAGES; s++) { mbar_init(BAR_FULL(s), 1); mbar_init(BAR_EMPTY(s), 1); }
-        mbar_init(BAR_SFULL, 1); mbar_init(BAR_SFULL + 8, 1);
-        mbar_init(BAR_RREADY, 128); mbar_init(BAR_RREADY + 8, 128);
+        for (int s = 0; s < C::NSLOT; s++) { mbar_init(BAR_SFULL + 8u * s, 1); mbar_init(BAR_RREADY + 8u * s, 128); }
         mbar_init(BAR_GFULL, 1);
         mbar_init(BAR_UREADY, 256);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -509,7 +532,7 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        if (elect_one()) {
             uint32_t stage = 0, phase = 0;
             for (int64_t w = blockIdx.x; w < n_items; w += gridDim.x) {
                 const int chunk = (int)(w / a.owner_tiles);
@@ -517,13 +540,19 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
                 const int nst = (int)min((int64_t)a.chunk_steps, a.stream_steps - t0);
                 for (int t = 0; t < nst; t++) {
                     if (!mbar_wait(BAR_EMPTY(stage), phase ^ 1, abort_flag, 1)) break;
-                    mbar_expect_tx(BAR_FULL(stage), C::TILE_BYTES);
                     const uint32_t dst = smem_base + stage * C::TILE_BYTES;
-                    const int row0 = (int)((t0 + t) * 128);
+                    const int row0 = (int)((t0 + t) * C::STEP_ROWS);
+                    if (a.dbg_flags & 2) { mbar_arrive(BAR_FULL(stage)); }
+                    else if (a.dbg_flags & 1) {
+                        mbar_expect_tx(BAR_FULL(stage), C::PART_BYTES);
+                        for (int kb = 0; kb < C::KB; kb++) tma_load_2d(dst + kb * C::BLOCK_BYTES, &tmHi, kb * 64, row0, BAR_FULL(stage));
+                    } else {
+                    mbar_expect_tx(BAR_FULL(stage), C::TILE_BYTES);
 #pragma unroll
                     for (int kb = 0; kb < C::KB; kb++) {
                         tma_load_2d(dst + kb * C::BLOCK_BYTES, &tmHi, kb * 64, row0, BAR_FULL(stage));
                         tma_load_2d(dst + C::PART_BYTES + kb * C::BLOCK_BYTES, &tmLo, kb * 64, row0, BAR_FULL(stage));
+                    }
                     }
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -532,35 +561,20 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t IDESC1 = make_idesc(128, 128, 0);
+        // One elected thread; everything it touches is kept in registers (no indexed arrays)
+        // and descriptors are formed as {base_lo + constant, constant_hi}: the thread's own
+        // instruction stream must stay well below the tensor time of a step.
+        if (elect_one()) {
+            constexpr uint32_t IDESC1 = make_idesc(128, C::STEP_ROWS, 0);
             constexpr uint32_t IDESC2 = make_idesc(128, KP, 1);
-            uint32_t stage = 0, phase = 0;      // smem ring (consumer side)
-            uint32_t rr_phase[2] = {0, 0};
+            // descriptor high words: SBO = 1024 B, version 1, SWIZZLE_128B (see make_desc)
+            constexpr uint32_t DHI = (1024u >> 4) | (1u << 14) | (2u << 29);
+            constexpr uint32_t DLO1 = (16u >> 4) << 16;                    // K-major: LBO field = 1
+            constexpr uint32_t DLO2 = ((uint32_t)C::BLOCK_BYTES >> 4) << 16; // MN-major: LBO = k-block stride
+            uint32_t s_stage = 0, s_phase = 0;   // smem ring position of the next tile to run stage 1 on
+            uint32_t g_stage = 0;                // ... of the next tile to run stage 2 on
+            uint32_t rr_phase = 0;               // bit per slot
             uint32_t u_phase = 0;
-            // stage 1: S^g = U_hi . W_hi^T   (single pass; see DESIGN.md for why no lo term)
-            auto issue_stage1 = [&](uint32_t sbase, int g) {
-                const uint32_t d = tmem + (g ? C::COL_S1 : C::COL_S0);
-#pragma unroll
-                for (int kk = 0; kk < KP / 16; kk++) {
-                    const uint32_t baddr = sbase + (kk >> 2) * C::BLOCK_BYTES + (kk & 3) * 32;
-                    tc_mma_ts(d, tmem + C::COL_U + kk * 8, make_desc(baddr, 16, 1024), IDESC1, kk ? 1u : 0u);
-                }
-            };
-            // stage 2: G += R^g . (W_hi + W_lo)   (B operand MN-major: N = k contiguous)
-            auto issue_stage2 = [&](uint32_t sbase, int g, bool first) {
-                const uint32_t rcol = tmem + (g ? C::COL_S1 : C::COL_S0);
-#pragma unroll
-                for (int p = 0; p < 2; p++) {
-#pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        const uint32_t baddr = sbase + p * C::PART_BYTES + j * (16 * 128);
-                        tc_mma_ts(tmem + C::COL_G, rcol + j * 8, make_desc(baddr, C::BLOCK_BYTES, 1024), IDESC2,
-                                  (first && p == 0 && j == 0) ? 0u : 1u);
-                    }
-                }
-            };
-            uint32_t sb_ring[3]; uint32_t st_ring[3];   // tiles t, t+1, t+2 (indexed t % 3)
             for (int64_t w = blockIdx.x; w < n_items; w += gridDim.x) {
                 const int chunk = (int)(w / a.owner_tiles);
                 const int64_t t0 = (int64_t)chunk * a.chunk_steps;
@@ -568,25 +582,36 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
                 bool ok = mbar_wait(BAR_UREADY, u_phase, abort_flag, 2);
                 u_phase ^= 1;
                 tc_fence_after();
-                auto acquire = [&](int t) {   // wait for tile t, remember its stage, issue S(t)
-                    ok = ok && mbar_wait(BAR_FULL(stage), phase, abort_flag, 3);
+                auto stage1 = [&](int t) {   // wait for tile t, S(slot t&3) = U_hi . W_hi^T
+                    ok = ok && mbar_wait(BAR_FULL(s_stage), s_phase, abort_flag, 3);
                     tc_fence_after();
-                    sb_ring[t % 3] = smem_base + stage * C::TILE_BYTES;
-                    st_ring[t % 3] = stage;
-                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
-                    issue_stage1(sb_ring[t % 3], t & 1);
-                    tc_commit(BAR_SFULL + 8u * (t & 1));
+                    const uint32_t lo = (((smem_base + s_stage * C::TILE_BYTES) >> 4) & 0x3FFFu) | DLO1;
+                    const uint32_t d = tmem + C::COL_S + 64 * (t & 3);
+#pragma unroll
+                    for (int kk = 0; kk < KP / 16; kk++)
+                        tc_mma_ts2(d, tmem + C::COL_U + kk * 8,
+                                   lo + (((kk >> 2) * C::BLOCK_BYTES + (kk & 3) * 32) >> 4), DHI, IDESC1, kk ? 1u : 0u);
+                    tc_commit(BAR_SFULL + 8u * (t & 3));
+                    if (++s_stage == C::STAGES) { s_stage = 0; s_phase ^= 1; }
                 };
-                acquire(0);
-                if (nst > 1) acquire(1);
+                for (int t = 0; t < C::NSLOT && t < nst; t++) stage1(t);
                 for (int t = 0; t < nst && ok; t++) {
-                    const int g = t & 1;
-                    ok = ok && mbar_wait(BAR_RREADY + 8u * g, rr_phase[g], abort_flag, 4);
-                    rr_phase[g] ^= 1;
+                    const int slot = t & 3;
+                    ok = ok && mbar_wait(BAR_RREADY + 8u * slot, (rr_phase >> slot) & 1u, abort_flag, 4);
+                    rr_phase ^= 1u << slot;
                     tc_fence_after();
-                    issue_stage2(sb_ring[t % 3], g, t == 0);
-                    tc_commit(BAR_EMPTY(st_ring[t % 3]));   // tile t fully consumed
-                    if (t + 2 < nst) acquire(t + 2);
+                    // stage 2: G += R(slot) . (W_hi + W_lo), B operand MN-major (N = k contiguous)
+                    const uint32_t lo = (((smem_base + g_stage * C::TILE_BYTES) >> 4) & 0x3FFFu) | DLO2;
+                    const uint32_t rcol = tmem + C::COL_S + 64 * slot;
+#pragma unroll
+                    for (int p = 0; p < 2; p++)
+#pragma unroll
+                        for (int j = 0; j < C::STEP_ROWS / 16; j++)
+                            tc_mma_ts2(tmem + C::COL_G, rcol + j * 8, lo + ((p * C::PART_BYTES + j * (16 * 128)) >> 4), DHI,
+                                       IDESC2, (t == 0 && p == 0 && j == 0) ? 0u : 1u);
+                    tc_commit(BAR_EMPTY(g_stage));   // tile t fully consumed
+                    if (++g_stage == C::STAGES) g_stage = 0;
+                    if (t + C::NSLOT < nst) stage1(t + C::NSLOT);
                 }
                 tc_commit(BAR_GFULL);
                 if (!ok) break;
@@ -598,10 +623,9 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
         const int q = warp & 3;                     // TMEM lane quarter
         const int lrow = q * 32 + lane;             // owner lane within the tile
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-        const uint32_t t_s = tmem + lane_addr + (grp ? C::COL_S1 : C::COL_S0);
-        const uint32_t bar_sfull = BAR_SFULL + 8u * grp, bar_rready = BAR_RREADY + 8u * grp;
-        uint32_t sf_phase = 0, g_phase = 0;
+        uint32_t sf_phase = 0, g_phase = 0;         // sf_phase: bit per slot
         const float c0 = exp2f((float)(eU + eW - 14));
+        const float finf = __int_as_float(0x7f800000);
         double log_acc_total = 0.0;
         bool first_item = true, ok = true;
         int64_t prev_w = -1;
@@ -659,8 +683,8 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
             const uint32_t bsel = ROWS ? 0u : (uint32_t)(l & 1);
             const uint32_t *vrow = a.vbits + orow * a.words;
             const uint32_t *mrow = a.mbits + orow * a.words;
-            // words per step: ROWS: 64 n -> 2 words; COLS: 128 f -> 4 words
-            constexpr int WPS = ROWS ? 2 : 4;
+            // bits per step: ROWS: 32 n -> 1 word; COLS: 64 f -> 2 words
+            constexpr int WPS = ROWS ? 1 : 2;
             uint32_t bv[WPS], bm[WPS];
             auto load_bits = [&](int t) {
                 const int64_t wi = (t0 + t) * WPS;
@@ -672,6 +696,8 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
             };
             if (grp < nst) load_bits(grp);
             for (int t = grp; t < nst && ok; t += 2) {
+                const int slot = t & 3;
+                const uint32_t t_s = tmem + lane_addr + C::COL_S + 64 * slot;
                 uint32_t sel[WPS], vv[WPS];
 #pragma unroll
                 for (int i = 0; i < WPS; i++) {
@@ -679,48 +705,52 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
                     sel[i] = ROWS ? bm[i] : ((bsel ? bv[i] : ~bv[i]) & bm[i]);
                 }
                 if (t + 2 < nst) load_bits(t + 2);
-                ok = ok && mbar_wait(bar_sfull, sf_phase, abort_flag, 8);
-                sf_phase ^= 1;
+                ok = ok && mbar_wait(BAR_SFULL + 8u * slot, (sf_phase >> slot) & 1u, abort_flag, 8);
+                sf_phase ^= 1u << slot;
                 tc_fence_after();
-#pragma unroll
-                for (int cc = 0; cc < 4; cc++) {
-                    uint32_t s[32], rp[16];
-                    tc_ld32(t_s + cc * 32, s);
-                    tc_wait_ld();
-                    if (a.dbg && w == 0 && t < 2) {
-#pragma unroll
-                        for (int i = 0; i < 32; i++) a.dbg[(lrow * 256) + t * 128 + cc * 32 + i] = __uint_as_float(s[i]);
+                uint32_t s0[32], s1[32];
+                tc_ld32(t_s, s0);
+                tc_ld32(t_s + 32, s1);
+                tc_wait_ld();
+                if (a.dbg != nullptr && w == 0 && t < 4) {
+                    for (int i = 0; i < 32; i++) {
+                        a.dbg[(lrow * 256) + t * 64 + i] = __uint_as_float(s0[i]);
+                        a.dbg[(lrow * 256) + t * 64 + 32 + i] = __uint_as_float(s1[i]);
                     }
+                }
+#pragma unroll
+                for (int cc = 0; cc < 2; cc++) {
+                    uint32_t (&s)[32] = cc ? s1 : s0;
+                    uint32_t rp[16];
                     if (ROWS) {
                         // 32 columns = 16 entries (n) x 2 branches, column 2j+b
-                        const uint32_t m16 = (sel[cc >> 1] >> ((cc & 1) * 16)) & 0xffffu;
-                        const uint32_t v16 = (vv[cc >> 1] >> ((cc & 1) * 16)) & 0xffffu;
+                        const uint32_t m16 = sel[0] >> (cc * 16);
+                        const uint32_t v16 = vv[0] >> (cc * 16);
 #pragma unroll
                         for (int j = 0; j < 16; j++) {
                             const bool vb = (v16 >> j) & 1u, mb = (m16 >> j) & 1u;
-                            const float sv = __uint_as_float(vb ? s[2 * j + 1] : s[2 * j]);
-                            float r = fminf(c0 * fast_rcp(sv), 65504.f);
-                            r = mb ? r : 0.f;
-                            if (a.want_log) log_acc += mb ? fast_lg2(sv) : 0.f;
-                            rp[j] = pack_h2(vb ? 0.f : r, vb ? r : 0.f);
+                            float sv = __uint_as_float(vb ? s[2 * j + 1] : s[2 * j]);
+                            if (WANT_LOG) log_acc += mb ? fast_lg2(sv) : 0.f;
+                            sv = mb ? sv : finf;                     // masked entry: R = 0
+                            const float r = c0 * fast_rcp(sv);
+                            rp[j] = pack_h2_sat(vb ? 0.f : r, vb ? r : 0.f);
                         }
                     } else {
                         const uint32_t m32 = sel[cc];
 #pragma unroll
                         for (int j = 0; j < 16; j++) {
-                            const float s0 = __uint_as_float(s[2 * j]), s1 = __uint_as_float(s[2 * j + 1]);
-                            const float r0 = ((m32 >> (2 * j)) & 1u) ? fminf(c0 * fast_rcp(s0), 65504.f) : 0.f;
-                            const float r1 = ((m32 >> (2 * j + 1)) & 1u) ? fminf(c0 * fast_rcp(s1), 65504.f) : 0.f;
-                            rp[j] = pack_h2(r0, r1);
+                            const float a0 = ((m32 >> (2 * j)) & 1u) ? __uint_as_float(s[2 * j]) : finf;
+                            const float a1 = ((m32 >> (2 * j + 1)) & 1u) ? __uint_as_float(s[2 * j + 1]) : finf;
+                            rp[j] = pack_h2_sat(c0 * fast_rcp(a0), c0 * fast_rcp(a1));
                         }
                     }
                     tc_st16(t_s + cc * 16, rp);
                 }
                 tc_wait_st();
                 tc_fence_before();
-                mbar_arrive(bar_rready);
+                mbar_arrive(BAR_RREADY + 8u * slot);
             }
-            log_acc_total += (double)log_acc;
+            if (WANT_LOG) log_acc_total += (double)log_acc;
         }
         // ---- drain G of the last item
         if (!first_item && ok) {
@@ -728,7 +758,7 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
             tc_fence_after();
             drain_G(prev_w);
         }
-        if (a.want_log) {
+        if (WANT_LOG) {
             double v = warp_sum(log_acc_total);
             if (lane == 0) atomicAdd(&a.dacc[0], v);
         }
@@ -760,13 +790,13 @@ __global__ void tp_logfix_kernel(const double *dacc, const int *dexp, double nse
         *sumlogD += 0.6931471805599453 * (dacc[0] - nsel * (double)(dexp[0] + dexp[1]));
 }
 
-template <int KP, bool ROWS>
+template <int KP, bool ROWS, bool WANT_LOG>
 static cudaError_t launch_tp(const CUtensorMap &tm, const CUtensorMap &tmlo, const TPArgs &a, int grid, cudaStream_t st)
 {
-    cudaError_t e = cudaFuncSetAttribute(tp_pass_kernel<KP, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(tp_pass_kernel<KP, ROWS, WANT_LOG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          TPCfg<KP>::SMEM_BYTES);
     if (e != cudaSuccess) return e;
-    tp_pass_kernel<KP, ROWS><<<grid, TP_THREADS, TPCfg<KP>::SMEM_BYTES, st>>>(tm, tmlo, a);
+    tp_pass_kernel<KP, ROWS, WANT_LOG><<<grid, TP_THREADS, TPCfg<KP>::SMEM_BYTES, st>>>(tm, tmlo, a);
     return cudaGetLastError();
 }
 
@@ -787,7 +817,7 @@ int tp_pass(nbmf_handle *h, int owner_rows, double *sumlogD)
         a.L = 2 * h->N; S_rows = h->F;
     }
     a.owner_tiles = (a.L + 127) / 128;
-    a.stream_steps = (S_rows + 127) / 128;
+    a.stream_steps = (S_rows + 63) / 64;
     a.chunk_steps = (int)std::min<int64_t>(s->chunk_steps, a.stream_steps);
     a.n_chunks = (int)((a.stream_steps + a.chunk_steps - 1) / a.chunk_steps);
     const int64_t Lpad = a.owner_tiles * 128;
@@ -805,12 +835,20 @@ int tp_pass(nbmf_handle *h, int owner_rows, double *sumlogD)
     a.dexp = s->dexp; a.dacc = s->dacc; a.derr = s->derr;
     a.want_log = (sumlogD != nullptr);
     a.dbg = g_tp_dbg;
+    { const char *f = getenv("NBMF_TP_DEBUG_FLAGS"); a.dbg_flags = f ? atoi(f) : 0; }
     if (a.want_log) cudaMemsetAsync(s->dacc, 0, 16, h->stream);
     const int64_t items = (int64_t)a.n_chunks * a.owner_tiles;
     const int grid = (int)std::min<int64_t>(items, h->sm_count);
     cudaError_t e;
-    if (KP == 128) e = owner_rows ? launch_tp<128, true>(s->tmB, s->tmBlo, a, grid, h->stream) : launch_tp<128, false>(s->tmA, s->tmAlo, a, grid, h->stream);
-    else e = owner_rows ? launch_tp<64, true>(s->tmB, s->tmBlo, a, grid, h->stream) : launch_tp<64, false>(s->tmA, s->tmAlo, a, grid, h->stream);
+    if (KP == 128) {
+        if (!owner_rows) e = launch_tp<128, false, false>(s->tmA, s->tmAlo, a, grid, h->stream);
+        else if (a.want_log) e = launch_tp<128, true, true>(s->tmB, s->tmBlo, a, grid, h->stream);
+        else e = launch_tp<128, true, false>(s->tmB, s->tmBlo, a, grid, h->stream);
+    } else {
+        if (!owner_rows) e = launch_tp<64, false, false>(s->tmA, s->tmAlo, a, grid, h->stream);
+        else if (a.want_log) e = launch_tp<64, true, true>(s->tmB, s->tmBlo, a, grid, h->stream);
+        else e = launch_tp<64, true, false>(s->tmB, s->tmBlo, a, grid, h->stream);
+    }
     if (e != cudaSuccess) { h->err = std::string("tp_pass launch: ") + cudaGetErrorString(e); return NBMF_ERR_CUDA; }
     tp_reduce_kernel<<<(unsigned)((a.L * KP + 255) / 256), 256, 0, h->stream>>>(s->partial, a.n_chunks, Lpad, a.L, KP, s->dexp,
                                                                               owner_rows ? 1 : 0, owner_rows ? h->GF : h->GN);
