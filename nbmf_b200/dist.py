@@ -1,0 +1,51 @@
+"""Column sharding of the VB / Gibbs hot path across the GPUs of one box
+(SURVEY.md section 8e): the N columns of V are split into contiguous blocks, one
+per rank; the Beta-side quantities (f_ones, f_zeros, B1, B0) of a block live only
+on its GPU; the Dirichlet-side statistic n_total (F x K) is replicated and is the
+one thing exchanged each iteration (all-reduce, sum).  One process per GPU,
+`torch.distributed` (NCCL over NVLink) is only the plumbing: the engine calls the
+hook below from inside its iteration loop with a device pointer.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_columns(N: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous column block [lo, hi) of rank `rank` out of `world`."""
+    if not (0 <= rank < world):
+        raise ValueError("rank out of range")
+    return (N * rank) // world, (N * (rank + 1)) // world
+
+
+def tensor_from_device_ptr(ptr: int, count: int, device):
+    """fp64 torch view of `count` doubles at device address `ptr` (no copy)."""
+    import torch
+
+    class _Arr:
+        pass
+    a = _Arr()
+    a.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+    return torch.as_tensor(a, device=device)
+
+
+def make_allreduce_hook(device, group=None):
+    """Hook for Engine.set_allreduce_hook: sums the buffer across ranks in place,
+    ordered on the engine's stream."""
+    import torch
+    import torch.distributed as dist
+
+    def hook(ptr: int, count: int, stream: int):
+        t = tensor_from_device_ptr(ptr, count, device)
+        with torch.cuda.stream(torch.cuda.ExternalStream(stream, device=device)):
+            dist.all_reduce(t, group=group)
+    return hook
+
+
+def combine_lowerbounds(terms3: np.ndarray, allreduce_sum) -> np.ndarray:
+    """Global ELBO trace from per-rank terms (nbmf_vb_get_lb_terms):
+    lb_i = sum_ranks(sum log D + (pH - qH)) + (pW - qW); the row term is replicated.
+    `allreduce_sum(x)` must return the sum over ranks of the fp64 array x."""
+    t = np.asarray(terms3, dtype=np.float64)
+    local = t[:, 0] + t[:, 2]
+    return allreduce_sum(local) + t[:, 1]

@@ -313,3 +313,23 @@ def test_synthetic_generator_and_properties():
     assert relF(W, ref["E_W"]) < 1e-10 and relF(H, ref["E_H"]) < 1e-10
     assert np.max(np.abs(lbs - ref["lowerbounds"]) / np.abs(ref["lowerbounds"])) < 1e-11
     e.close()
+
+
+# ---------------------------------------------------------------------------
+# against the golden vectors produced by the reference's own sources
+# (tests/golden/make_golden.py, oracle/ref_shim)
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("c", ["a", "b", "c"])
+def test_gpu_matches_reference_golden_vectors(c):
+    import os
+    from nbmf_b200 import VB_Aspect_Rcpp, VB_DirBer_Rcpp
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_vectors.npz"))
+    K, al, be, ga, it = G[f"aspect_{c}_par"]
+    V = G[f"aspect_{c}_V"]
+    got = VB_Aspect_Rcpp(V, G[f"aspect_{c}_Z"], int(K), al, be, ga, int(it), True)
+    assert relF(got["E_W"], G[f"aspect_{c}_E_W"]) < 1e-10 and relF(got["E_H"], G[f"aspect_{c}_E_H"]) < 1e-10
+    assert np.max(np.abs(got["lowerbounds"] - G[f"aspect_{c}_lowerbounds"]) / np.abs(G[f"aspect_{c}_lowerbounds"])) < 1e-11
+    assert np.max(np.abs(got["E_Z"] - G[f"aspect_{c}_E_Z"])) < 1e-10
+    d = VB_DirBer_Rcpp(V, G[f"dirber_{c}_Z"], int(K), al, be, ga, max(int(it) // 2, 2))
+    for k in ("E_W", "E_H", "E_Z"):
+        assert np.array_equal(d[k], G[f"dirber_{c}_{k}"], equal_nan=True), k

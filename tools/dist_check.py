@@ -1,0 +1,46 @@
+"""torchrun --nproc-per-node G tools/dist_check.py : column-sharded VB equals the single-GPU run."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from nbmf_b200 import Engine, _lib  # noqa: E402
+from nbmf_b200.dist import combine_lowerbounds, make_allreduce_hook, shard_columns  # noqa: E402
+
+rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+rel = lambda x, y: np.linalg.norm(x - y) / np.linalg.norm(y)
+for (F, N, K, prec, iters) in [(300, 1000, 5, _lib.PREC_FP64, 12), (2048, 4096, 128, _lib.PREC_TENSOR, 8), (1500, 3000, 64, _lib.PREC_AUTO, 6)]:
+    lo, hi = shard_columns(N, rank, world)
+    e = Engine(device=local, precision=prec, n_global=N, n_offset=lo)
+    e.generate_synthetic(F, hi - lo, 4, 1.0, 1.0, 21)
+    e.set_allreduce_hook(make_allreduce_hook(dev))
+    e.init_random_labels(K, 22)
+    W, H, _, _ = e.vb_aspect(K, 1.0, 1.0, 0.5, iter=iters, checklb=True)
+    terms = e.vb_lb_terms(iters)
+
+    def ar(x):
+        t = torch.tensor(x, device=dev, dtype=torch.float64); dist.all_reduce(t); return t.cpu().numpy()
+    lb = combine_lowerbounds(terms, ar)
+    Hs = [torch.zeros((N * (r + 1) // world - N * r // world, K), dtype=torch.float64, device=dev) for r in range(world)]
+    dist.all_gather(Hs, torch.tensor(np.ascontiguousarray(H), device=dev))
+    Hall = torch.cat(Hs).cpu().numpy()
+    e.close()
+    if rank == 0:
+        e1 = Engine(device=local, precision=prec)
+        e1.generate_synthetic(F, N, 4, 1.0, 1.0, 21)
+        e1.init_random_labels(K, 22)
+        W1, H1, lb1, _ = e1.vb_aspect(K, 1.0, 1.0, 0.5, iter=iters, checklb=True)
+        e1.close()
+        print(f"F={F} N={N} K={K} prec={prec} world={world}: relF E_W {rel(W, W1):.2e} E_H {rel(Hall, H1):.2e} "
+              f"ELBO {np.max(np.abs(lb - lb1) / np.abs(lb1)):.2e}", flush=True)
+        assert rel(W, W1) < 5e-6 and rel(Hall, H1) < 5e-6 and np.max(np.abs(lb - lb1) / np.abs(lb1)) < 5e-6
+    dist.barrier()
+if rank == 0:
+    print("dist_check ok")
+dist.destroy_process_group()
