@@ -1,0 +1,112 @@
+"""BASELINE.json configs 2 and 3 on their real data (fixtures under tests/golden/), through the
+C ABI, against the oracle (bit-identical to the reference's own sources, tests/test_oracle_pin.py)."""
+import numpy as np
+import pytest
+
+from oracle import oracle
+from tests import datasets
+
+pytestmark = pytest.mark.gpu
+NA = datasets.NA
+
+
+def relF(a, b):
+    return np.linalg.norm(a - b) / np.linalg.norm(b)
+
+
+def test_config2_unvotes100_vb_dirber_predictive_ll():
+    """VB_DirBer on unvotes100, 20 % of the observed entries held out, K=10: the exact wavefront
+    reproduces the reference bit for bit, and the predictive log-likelihood (R/commons.R:17-24)
+    matches."""
+    from nbmf_b200 import VB_DirBer, loglikelihood
+    V = datasets.unvotes100()
+    tr, te = datasets.hold_out(V, 0.2, 2)
+    K, iters = 10, 12
+    Z = oracle.random_labels(tr, K, 3)
+    Z1 = Z.copy(); Z1[Z1 != NA] += 1          # R passes 1-based labels; the wrapper zero-bases them
+    got = VB_DirBer(tr, Z1, K, 1.0, 1.0, 1.0, iters)
+    ref = oracle.vb_dirber(tr, Z, K, 1.0, 1.0, 1.0, iter=iters)
+    assert got["E_W"].shape == (100, K + 1) and got["E_H"].shape == (5429, K + 1)
+    assert np.array_equal(got["E_W"], ref["E_W"], equal_nan=True)
+    assert np.array_equal(got["E_H"], ref["E_H"], equal_nan=True)
+    ll = loglikelihood(got, te)
+    ll_ref, n = oracle.loglikelihood(ref["E_W"], ref["E_H"], te)
+    assert ll["n"] == n == int((te != NA).sum())
+    assert abs(ll["loglikelihood"] - ll_ref) < 1e-10 * abs(ll_ref)
+    assert -0.7 < ll["loglikelihood"] / n < -0.2      # sane: better than a coin, not degenerate
+
+
+@pytest.mark.parametrize("gamma", [1.0, 0.1])
+def test_config2_unvotes100_vb_aspect(gamma):
+    from nbmf_b200 import VB_aspectRcpp, loglikelihood
+    V = datasets.unvotes100()
+    tr, te = datasets.hold_out(V, 0.2, 2)
+    K, iters = 10, 40
+    Z = oracle.random_labels(tr, K, 5)
+    got = VB_aspectRcpp(tr, Z, K, 1.0, 1.0, gamma, iters, checklb=True)
+    ref = oracle.vb_aspect(tr, Z, K, 1.0, 1.0, gamma, iter=iters, checklb=True)
+    assert relF(got["E_W"], ref["E_W"]) < 1e-9 and relF(got["E_H"], ref["E_H"]) < 1e-9
+    assert np.max(np.abs(got["lowerbounds"] - ref["lowerbounds"]) / np.abs(ref["lowerbounds"])) < 1e-10
+    ll = loglikelihood(got, te)
+    ll_ref, n = oracle.loglikelihood(ref["E_W"], ref["E_H"], te)
+    assert abs(ll["loglikelihood"] - ll_ref) < 1e-9 * abs(ll_ref)
+
+
+def test_config3_mnist_gibbs_statistical_parity():
+    """Uncollapsed Gibbs (engine) vs the reference's collapsed sampler on MNIST columns, K=16,
+    gamma=1/16: posterior-mean E_V and predictive LL on 10 % held-out pixels agree within the
+    seed-to-seed spread."""
+    from nbmf_b200 import Gibbs_DirBer_finite_Rcpp
+    V = datasets.mnistbinary_2000()[:, :160]
+    F, N = V.shape
+    tr, te = datasets.hold_out(V, 0.1, 4)
+    test = te != NA
+    fi, ni = np.nonzero(test)
+    idx = (fi + F * ni).astype(np.int64)
+    vt = V[test]
+    K = 16
+    ll_ref, ll_gpu, ev_ref, ev_gpu = [], [], [], []
+    for s in (1, 2, 3):
+        Z = oracle.random_labels(tr, K, s)
+        c = oracle.gibbs_dirber_finite(tr, Z, K, 1.0, 1.0, 1.0 / 16, iter=120, burnin=0.5, seed=s)
+        _, _, EV = oracle.gibbs_expectation(tr, c["Z_samples"][:, :, :c["written"]], K, 1.0, 1.0, 1.0 / 16)
+        p = np.clip(EV[test], 1e-12, 1 - 1e-12)
+        ll_ref.append(np.mean(np.log(np.where(vt == 1, p, 1 - p)))); ev_ref.append(p)
+        g = Gibbs_DirBer_finite_Rcpp(tr, Z, K, 1.0, 1.0, 1.0 / 16, 800, 0.5, seed=s, test_idx=idx)
+        q = np.clip(g["E_V_test"], 1e-12, 1 - 1e-12)
+        ll_gpu.append(np.mean(np.log(np.where(vt == 1, q, 1 - q)))); ev_gpu.append(q)
+    spread = max(np.ptp(ll_ref), np.ptp(ll_gpu), 0.01)
+    assert abs(np.mean(ll_ref) - np.mean(ll_gpu)) < 2 * spread, (ll_ref, ll_gpu)
+    between = np.sqrt(np.mean((np.mean(ev_ref, 0) - np.mean(ev_gpu, 0)) ** 2))
+    within = np.sqrt(np.mean((ev_ref[0] - ev_ref[1]) ** 2))
+    assert between < 2 * max(within, 0.02), (between, within)
+    # both beat the marginal-frequency predictor
+    base = np.mean(np.log(np.where(vt == 1, V.mean(), 1 - V.mean())))
+    assert np.mean(ll_gpu) > base
+
+
+def test_config3_mnist_gibbs_full_fixture_runs():
+    """2000 MNIST columns, K=16, a short chain: counts stay consistent, E_W rows sum to 1."""
+    from nbmf_b200 import Engine
+    V = datasets.mnistbinary_2000()
+    e = Engine()
+    e.set_data(V)
+    e.init_random_labels(16, 3)
+    W, H, _, Z = e.gibbs_dirber(16, 1.0, 1.0, 1.0 / 16, iter=40, burnin=0.5, seed=9, want_Z=True)
+    tim = e.timing()
+    e.close()
+    assert np.allclose(W.sum(1), 1.0, atol=1e-9) and np.all((H > 0) & (H < 1))
+    assert Z.min() >= 0 and Z.max() < 16 and tim["iters"] == 39
+
+
+def test_bernoulli_nmf_entry_point_vb():
+    from nbmf_b200 import BernoulliNMF
+    V = datasets.unvotes100()[:, :400]
+    res = BernoulliNMF(V, K=5, model="aspectRcpp", method="VB", iter=15, seed=1)
+    assert res["E_W"].shape == (100, 5) and res["E_H"].shape == (400, 5)
+    res2 = BernoulliNMF(V, K=5, model="DirBer", method="VB", iter=5, seed=1)
+    assert res2["E_W"].shape == (100, 6)                     # K+1 columns (collapsed_gibbs_z_VB.cpp:101)
+    with pytest.raises(ValueError):
+        BernoulliNMF(V, K=5, model="DirBer", method="Gibbs", iter=5)   # K < K_init=10 (Appendix B.9)
+    res3 = BernoulliNMF(V[:, :120], K=10, model="DirBer", method="Gibbs", iter=30, burnin=0.5, seed=2)
+    assert res3["E_W"].shape == (100, 10) and res3["class"][0] == "GibbsDirBer"
