@@ -229,16 +229,26 @@ def main():
         vb_host = pv.numpy().view(np.uint32)
         del v, m
         eng.init_random_labels(K, wl["seed"] + 1)
-        st = eng.get_stats(K)
+
+        def pinned(shape):   # column-major fp64 view of pinned host memory
+            t = torch.empty(int(np.prod(shape)), dtype=torch.float64, pin_memory=True)
+            return t.numpy().reshape(shape, order="F")
+        st = tuple(pinned(x.shape) for x in eng.get_stats(K))
+        for dst, src in zip(st, eng.get_stats(K)):
+            dst[...] = src
+        outW, outH = pinned((F, K)), pinned((Nl, K))
         steps_e = max(1, args.e2e_steps)
         h2d = vb_host.nbytes + sum(x.nbytes for x in st)
         d2h = (F * K + Nl * K) * 8 + 8
+        # one untimed call so that buffers exist (a user's second call onward looks like this)
+        eng.set_data_bits(vb_host, None, F, Nl); eng.set_stats(*st)
+        eng.vb_aspect(K, 1.0, 1.0, wl["gamma"], iter=1, checklb=True, out=(outW, outH))
         barrier()
         t0 = time.perf_counter()
         for _ in range(steps_e):
             eng.set_data_bits(vb_host, None, F, Nl)
             eng.set_stats(*st)
-            eng.vb_aspect(K, 1.0, 1.0, wl["gamma"], iter=1, checklb=True)
+            eng.vb_aspect(K, 1.0, 1.0, wl["gamma"], iter=1, checklb=True, out=(outW, outH))
         barrier()
         dt = time.perf_counter() - t0
         if world > 1:

@@ -148,6 +148,13 @@ int nbmf_vb_end(nbmf_handle *h, double *E_W, double *E_H, double *lowerbounds, i
  * pH - qH (the handle's columns).  lowerbounds[i] of nbmf_vb_end is their sum. */
 int nbmf_vb_get_lb_terms(nbmf_handle *h, double *terms3, int n_iter);
 
+/* ---- which.max hand-off (R/BernoulliNMF.R:45-52) ------------------------------
+ * Z_fn <- argmax_k E_Z(f,k,n) from the operands of the last VB iteration, computed on
+ * the device without the E_Z cube; the labels stay on the device for a following
+ * nbmf_gibbs_dirber and are copied to Z_out (F x N, 0-based, NA where V is NA) if
+ * it is non-NULL.                                                               */
+int nbmf_vb_argmax_labels(nbmf_handle *h, int32_t *Z_out);
+
 /* ---- lower_bound_aspect (collapsed_gibbs_z_VB.cpp:339-369) -----------------
  * ELBO of the current statistics' parameters with q(Z) at its optimum, and its
  * seven-term split (pW,pZ+pV-qZ,pH,0,qW,0,qH) for diagnostics.                */

@@ -61,6 +61,7 @@ SYMBOLS = {
     "nbmf_vb_step": (C.c_int, [_H, C.c_int]),
     "nbmf_vb_end": (C.c_int, [_H, _dp, _dp, _dp, C.c_int, _dp]),
     "nbmf_vb_get_lb_terms": (C.c_int, [_H, _dp, C.c_int]),
+    "nbmf_vb_argmax_labels": (C.c_int, [_H, _ip]),
     "nbmf_lower_bound": (C.c_int, [_H, C.c_int, C.c_double, C.c_double, C.c_double, _dp, _dp]),
     "nbmf_vb_dirber": (C.c_int, [_H, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, _dp, _dp, _dp]),
     "nbmf_gibbs_dirber": (C.c_int, [_H, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_double,

@@ -167,8 +167,13 @@ class Engine:
         return nt, fo, fz
 
     # -- VB --------------------------------------------------------------
-    def vb_aspect(self, K, alpha=1.0, beta=1.0, gamma=1.0, iter=100, checklb=False, return_E_Z=False):
-        E_W = np.zeros((self.F, K), order="F"); E_H = np.zeros((self.N, K), order="F")
+    def vb_aspect(self, K, alpha=1.0, beta=1.0, gamma=1.0, iter=100, checklb=False, return_E_Z=False, out=None):
+        """`out=(E_W, E_H)`: caller-owned column-major fp64 buffers (e.g. pinned memory)."""
+        if out is not None:
+            E_W, E_H = out
+            assert E_W.shape == (self.F, K) and E_H.shape == (self.N, K) and E_W.flags.f_contiguous and E_H.flags.f_contiguous
+        else:
+            E_W = np.zeros((self.F, K), order="F"); E_H = np.zeros((self.N, K), order="F")
         lbs = np.zeros(max(iter, 1))
         E_Z = np.zeros((self.F, K, self.N), order="F") if return_E_Z else None
         self._ck(self.lib.nbmf_vb_aspect(self.h, K, alpha, beta, gamma, iter, int(checklb), _ptr(E_W, _dp),
@@ -194,6 +199,12 @@ class Engine:
         t = np.zeros((max(n_iter, 1), 3))
         self._ck(self.lib.nbmf_vb_get_lb_terms(self.h, _ptr(t, _dp), n_iter))
         return t[:n_iter]
+
+    def argmax_labels(self, want_host=False):
+        """which.max(E_Z[f,,n]) of the last VB iteration, kept on the device (BernoulliNMF.R:45-52)."""
+        Z = np.zeros((self.F, self.N), dtype=np.int32, order="F") if want_host else None
+        self._ck(self.lib.nbmf_vb_argmax_labels(self.h, _ptr(Z, _ip)))
+        return Z
 
     def lower_bound(self, K, alpha=1.0, beta=1.0, gamma=1.0):
         lb = C.c_double(0.0)
@@ -398,13 +409,19 @@ def BernoulliNMF(V, K, K_init=None, model="DirBer", method="Gibbs", alpha=1.0, b
         if K < 10:
             raise ValueError("K < K_init=10: the reference would write counters out of bounds "
                              "(BernoulliNMF.R:18-20, SURVEY.md Appendix B.9)")
-        warm = VB_aspectRcpp(Vi, Z, K_init, alpha, beta, gamma, 100, device=device)
-        E_Z = warm["E_Z"]
-        if E_Z is None:
-            raise MemoryError("warm-start E_Z too large")
-        Zw = np.asfortranarray(np.argmax(E_Z, axis=1).astype(np.int32) + 1)  # which.max, 1-based
-        Zw[Vi == NA_INTEGER] = NA_INTEGER
-        res = Gibbs_DirBer(Vi, Zw, K, alpha, beta, gamma, iter, burnin, seed=seed, device=device)
+        # warm start and which.max hand-off on the device: no E_Z cube crosses the boundary
+        e = Engine(device=device)
+        try:
+            e.set_data(Vi)
+            e.init_from_labels(_zero_base(Z), K_init)
+            e.vb_aspect(K_init, alpha, beta, gamma, iter=100)
+            e.argmax_labels()
+            E_W, E_H, E_V, Zl = e.gibbs_dirber(K, alpha, beta, gamma, iter, burnin, seed, None, want_Z=True)
+        finally:
+            e.close()
+        res = {"E_W": E_W, "E_H": E_H, "E_V_test": E_V, "Z_last": Zl, "V": Vi, "alpha": alpha, "beta": beta,
+               "gamma": gamma, "class": ("GibbsDirBer", "Bernoulli")}
+        _check_nonneg(res)
     elif method == "VB":
         if model == "aspectRcpp" or model == "aspect":
             res = VB_aspectRcpp(Vi, Z, K, alpha, beta, gamma, iter, device=device)

@@ -35,6 +35,7 @@ struct nbmf_handle {
     bool has_na = false;
 
     int Kc = 0, Kp = 0, KC = 0, NKC = 0;
+    int Kp_alloc_K = 0;                          // K the model buffers were sized for (Kc = 0 marks 'statistics stale')
     double *statF = nullptr, *statN = nullptr;   // current statistics
     double *A = nullptr, *BB = nullptr;          // operands of the current iteration
     double *GF = nullptr, *GN = nullptr;         // raw contraction outputs

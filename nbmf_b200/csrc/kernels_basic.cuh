@@ -394,6 +394,48 @@ __global__ void ez_aspect_kernel(const double *__restrict__ A, const double *__r
     for (int k = 0; k < K; k++) EZ[f + F * k + F * (int64_t)K * n] = obs ? a[k] * b[k] / d : 0.0;
 }
 
+// Z_fn <- which.max(E_Z[f,,n]) (BernoulliNMF.R:45-52, the Gibbs warm start) without the
+// E_Z cube: argmax_k A_fk B^{v}_nk from the operands of the last VB iteration; first maximum
+// wins, as which.max does.  NA where V is NA.
+__global__ void argmax_labels_kernel(const double *__restrict__ A, const double *__restrict__ BB,
+                                     const uint32_t *__restrict__ vc, const uint32_t *__restrict__ mc,
+                                     int64_t F, int64_t N, int64_t Fw, int K, int Kp, int32_t *__restrict__ Z)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= F * N) return;
+    int64_t f = i % F, n = i / F;
+    uint32_t mw = mc ? mc[n * Fw + (f >> 5)] : 0xffffffffu;
+    if (!((mw >> (f & 31)) & 1u)) { Z[i] = NBMF_NA_INTEGER; return; }
+    int v = (vc[n * Fw + (f >> 5)] >> (f & 31)) & 1u;
+    const double *a = A + f * Kp, *b = BB + (2 * n + v) * Kp;
+    int best = 0;
+    double bv = a[0] * b[0];
+    for (int k = 1; k < K; k++) {
+        double p = a[k] * b[k];
+        if (p > bv) { bv = p; best = k; }
+    }
+    Z[i] = best;
+}
+
+__global__ void f64_stats_to_counts_kernel(const double *__restrict__ statF, const double *__restrict__ statN,
+                                           int64_t F, int64_t N, int K, int Kp, int32_t *__restrict__ cF,
+                                           int32_t *__restrict__ cN)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < F * K) cF[i] = (int32_t)llrint(statF[(i / K) * Kp + (i % K)]);
+    if (i < 2 * N * K) cN[i] = (int32_t)llrint(statN[(i / K) * Kp + (i % K)]);
+}
+__global__ void i32_to_f64_kernel(const int32_t *__restrict__ a, int64_t n, double *__restrict__ b)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) b[i] = (double)a[i];
+}
+__global__ void f64_to_i32_kernel(const double *__restrict__ a, int64_t n, int32_t *__restrict__ b)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) b[i] = (int32_t)llrint(a[i]);
+}
+
 // ---------------------------------------------------------------------------
 // VB_DirBer_Rcpp sweep (collapsed_gibbs_z_VB.cpp:119-141) on the anti-diagonal
 // wavefront d = f + n: entries of one diagonal touch disjoint counter rows, and

@@ -81,7 +81,7 @@ static void free_model(nbmf_handle *h)
     cudaFree(h->GF); cudaFree(h->GN); cudaFree(h->EW); cudaFree(h->EH);
     h->statF = h->statN = h->A = h->BB = h->GF = h->GN = h->EW = h->EH = nullptr;
     tp_free(h);
-    h->Kc = h->Kp = 0;
+    h->Kc = h->Kp = 0; h->Kp_alloc_K = 0;
 }
 
 extern "C" void nbmf_destroy(nbmf_handle *h)
@@ -152,6 +152,15 @@ static int exchange(nbmf_handle *h, double *buf, size_t count)
 static int alloc_planes(nbmf_handle *h, int64_t F, int64_t N)
 {
     CK(cudaSetDevice(h->device));
+    if (h->vc && h->F == F && h->N == N) { // same shape (e.g. one C-ABI call per VB iteration): keep every buffer
+        size_t cb0 = (size_t)N * h->Fw * 4, rb0 = (size_t)F * h->Nw * 4;
+        cudaFree(h->Z); h->Z = nullptr;
+        h->nobs = 0;
+        CK(cudaMemsetAsync(h->vc, 0, cb0, h->stream)); CK(cudaMemsetAsync(h->mc, 0, cb0, h->stream));
+        CK(cudaMemsetAsync(h->vr, 0, rb0, h->stream)); CK(cudaMemsetAsync(h->mr, 0, rb0, h->stream));
+        tp_invalidate_data(h);
+        return NBMF_OK;
+    }
     free_data(h);
     free_model(h);
     h->F = F; h->N = N; h->nobs = 0;
@@ -315,9 +324,15 @@ static int ensure_model(nbmf_handle *h, int Kc)
     if (Kc <= 0 || Kc > 512) return fail(h, NBMF_ERR_ARG, "K must be in 1..512");
     if (h->Kc == Kc && h->statF) return NBMF_OK;
     CK(cudaSetDevice(h->device));
+    if (h->statF && h->Kp_alloc_K == Kc) { // buffers of the right size exist: only reset the statistics
+        h->Kc = Kc;
+        CK(cudaMemsetAsync(h->statF, 0, (size_t)h->F * h->Kp * 8, h->stream));
+        CK(cudaMemsetAsync(h->statN, 0, (size_t)2 * h->N * h->Kp * 8, h->stream));
+        return NBMF_OK;
+    }
     free_model(h);
     choose_kchunks(Kc, &h->KC, &h->NKC);
-    h->Kc = Kc; h->Kp = h->KC * h->NKC;
+    h->Kc = Kc; h->Kp = h->KC * h->NKC; h->Kp_alloc_K = Kc;
     size_t fb = (size_t)h->F * h->Kp * 8, nb = (size_t)2 * h->N * h->Kp * 8;
     if (cudaMalloc(&h->statF, fb) != cudaSuccess || cudaMalloc(&h->statN, nb) != cudaSuccess ||
         cudaMalloc(&h->A, fb) != cudaSuccess || cudaMalloc(&h->BB, nb) != cudaSuccess ||
@@ -378,7 +393,7 @@ extern "C" int nbmf_init_random_labels(nbmf_handle *h, int Kc, uint64_t seed)
     if (rc) return rc;
     const int64_t F = h->F, N = h->N;
     cudaFree(h->Z); h->Z = nullptr;
-    if ((double)F * N * 4 <= 2e9) {
+    if ((double)F * N * 4 <= 8e9) {
         if (cudaMalloc(&h->Z, (size_t)F * N * 4) != cudaSuccess) { cudaGetLastError(); h->Z = nullptr; }
     }
     hist_random_cols_kernel<<<(unsigned)N, 256, 2 * Kc * sizeof(int), h->stream>>>(
@@ -666,6 +681,23 @@ extern "C" int nbmf_vb_aspect(nbmf_handle *h, int K, double alpha, double beta, 
     return nbmf_vb_end(h, E_W, E_H, lowerbounds, iter, E_Z);
 }
 
+extern "C" int nbmf_vb_argmax_labels(nbmf_handle *h, int32_t *Z_out)
+{
+    if (!h) return NBMF_ERR_ARG;
+    if (!h->A || !h->BB || h->Kc <= 0) return fail(h, NBMF_ERR_STATE, "no VB operands: run nbmf_vb_aspect / nbmf_vb_step first");
+    if (h->hook) return fail(h, NBMF_ERR_UNSUPPORTED, "argmax labels under column sharding: call per rank on its own block");
+    CK(cudaSetDevice(h->device));
+    const int64_t F = h->F, N = h->N;
+    if ((double)F * N * 4 > 64e9) return fail(h, NBMF_ERR_UNSUPPORTED, "label matrix too large");
+    cudaFree(h->Z); h->Z = nullptr;
+    if (cudaMalloc(&h->Z, (size_t)F * N * 4) != cudaSuccess) { cudaGetLastError(); return fail(h, NBMF_ERR_OOM, "label allocation failed"); }
+    argmax_labels_kernel<<<nblk(F * N, 256), 256, 0, h->stream>>>(h->A, h->BB, h->vc, h->mc, F, N, h->Fw, h->Kc, h->Kp, h->Z);
+    LAUNCH_CHECK();
+    if (Z_out) CK(cudaMemcpyAsync(Z_out, h->Z, (size_t)F * N * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return NBMF_OK;
+}
+
 extern "C" int nbmf_lower_bound(nbmf_handle *h, int K, double alpha, double beta, double gamma,
                                 double *lb, double *terms7)
 {
@@ -810,7 +842,6 @@ extern "C" int nbmf_gibbs_dirber(nbmf_handle *h, int K, double alpha, double bet
     if (!h) return NBMF_ERR_ARG;
     if (!h->vc) return fail(h, NBMF_ERR_STATE, "no data");
     if (K <= 0 || K > 256) return fail(h, NBMF_ERR_ARG, "Gibbs: K must be in 1..256");
-    if (h->hook) return fail(h, NBMF_ERR_UNSUPPORTED, "column-sharded Gibbs is not wired yet (int32 count allreduce)");
     if (!(alpha > 0) || !(beta > 0) || !(gamma > 0)) return fail(h, NBMF_ERR_ARG, "priors must be > 0");
     CK(cudaSetDevice(h->device));
     const int64_t F = h->F, N = h->N;
@@ -824,6 +855,15 @@ extern "C" int nbmf_gibbs_dirber(nbmf_handle *h, int K, double alpha, double bet
     A1((void **)&cF, fk * 4); A1((void **)&cN, 2 * nk * 4);
     A1((void **)&W, fk * 4); A1((void **)&H, nk * 4); A1((void **)&wc, fk * 4); A1((void **)&hc, nk * 4);
     A1((void **)&accW, fk * 8); A1((void **)&accH, nk * 8); A1((void **)&outb, std::max(fk, nk) * 8);
+    // column sharding: the row counts n_total (F x K) are the one thing exchanged per sweep; the
+    // hook sums fp64, so the int32 counts take a round trip through `outb`
+    auto exchange_counts = [&]() -> cudaError_t {
+        if (!h->hook) return cudaSuccess;
+        i32_to_f64_kernel<<<nblk((int64_t)fk, 256), 256, 0, h->stream>>>(cF, (int64_t)fk, outb);
+        if (h->hook(h->hook_ctx, (void *)outb, fk, (void *)h->stream) != 0) return cudaErrorUnknown;
+        f64_to_i32_kernel<<<nblk((int64_t)fk, 256), 256, 0, h->stream>>>(outb, (int64_t)fk, cF);
+        return cudaGetLastError();
+    };
     if (n_test > 0) { A1((void **)&accV, (size_t)n_test * 8); A1((void **)&didx, (size_t)n_test * 8); }
     if (Z_last) A1((void **)&Zd, (size_t)F * N * 4);
     int rc = NBMF_OK;
@@ -850,6 +890,13 @@ extern "C" int nbmf_gibbs_dirber(nbmf_handle *h, int K, double alpha, double bet
             if (e == cudaSuccess) e = cudaMemcpyAsync(&bad, cnt + 1, 8, cudaMemcpyDeviceToHost, h->stream);
             if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
             if (e == cudaSuccess && bad) { rc = fail(h, NBMF_ERR_ARG, "Z contains labels outside 0..K-1 (BernoulliNMF.R:18-20 forces K_init=10)"); }
+            if (e == cudaSuccess && rc == NBMF_OK) e = exchange_counts();
+        } else if (h->statF && h->Kc == K) {
+            // no label matrix on the device (too large): the statistics of a label initialisation
+            // are the integer counts themselves
+            f64_stats_to_counts_kernel<<<nblk((int64_t)std::max(fk, 2 * nk), 256), 256, 0, h->stream>>>(
+                h->statF, h->statN, F, N, K, h->Kp, cF, cN);
+            e = cudaGetLastError();
         } else {
             rc = fail(h, NBMF_ERR_STATE, "Gibbs needs labels: call nbmf_init_from_labels or nbmf_init_random_labels first");
         }
@@ -867,6 +914,7 @@ extern "C" int nbmf_gibbs_dirber(nbmf_handle *h, int K, double alpha, double bet
             cudaMemsetAsync(cN, 0, 2 * nk * 4, h->stream);
             gibbs_sweep_kernel<<<sgrid, 256, smem_sweep, h->stream>>>(h->vc, h->has_na ? h->mc : nullptr, F, N, h->Fw, h->opts.n_offset, K, W, H, seed, (uint32_t)i, cF, cN, (i == iter - 1) ? Zd : nullptr);
             h->timing.launches += 5;
+            if (e == cudaSuccess) e = exchange_counts();
             if (i >= nburnin) {
                 gibbs_accumulate_kernel<<<nblk(std::max(F, N), 256), 256, 0, h->stream>>>(cF, cN, F, N, K, alpha, beta, gamma, accW, accH, wc, hc);
                 if (n_test > 0)

@@ -81,6 +81,12 @@ bool tp_supported(const nbmf_handle *h)
     return true;
 }
 
+void tp_invalidate_data(nbmf_handle *h)
+{
+    TPState *s = (TPState *)h->tp;
+    if (s) s->counts_ready = false;
+}
+
 void tp_free(nbmf_handle *h)
 {
     TPState *s = (TPState *)h->tp;

@@ -9,5 +9,6 @@ int tp_convert_operands(nbmf_handle *h);      // A, BB (fp64) -> scaled f16 hi/l
 int tp_pass(nbmf_handle *h, int owner_rows, double *sumlogD);
 int tp_log_correction(nbmf_handle *h, int owner_rows, double *sumlogD); // call after each pass, before the exchange
 int tp_finalize(nbmf_handle *h);            // statistics = U (.) G with exact-count row normalisation
+void tp_invalidate_data(nbmf_handle *h);     // V changed under the same shape: recount on next use
 void tp_free(nbmf_handle *h);
 int tp_check_error(nbmf_handle *h);         // reports (and clears) a kernel-side barrier timeout

@@ -333,3 +333,22 @@ def test_gpu_matches_reference_golden_vectors(c):
     d = VB_DirBer_Rcpp(V, G[f"dirber_{c}_Z"], int(K), al, be, ga, max(int(it) // 2, 2))
     for k in ("E_W", "E_H", "E_Z"):
         assert np.array_equal(d[k], G[f"dirber_{c}_{k}"], equal_nan=True), k
+
+
+def test_argmax_labels_hand_off_matches_which_max():
+    """BernoulliNMF.R:45-52: Z <- which.max(E_Z[f,,n]) after the VB warm start, on the device."""
+    from nbmf_b200 import Engine
+    V = make_problem(45, 60, 3, 12, 0.15)
+    K = 6
+    Z = oracle.random_labels(V, K, 2)
+    ref = oracle.vb_aspect(V, Z, K, 1.0, 1.0, 0.5, iter=9, return_E_Z=True)
+    e = Engine(); e.set_data(V); e.init_from_labels(Z, K)
+    e.vb_aspect(K, 1.0, 1.0, 0.5, iter=9)
+    Zg = e.argmax_labels(want_host=True)
+    e.close()
+    obs = V != NA
+    want = np.argmax(ref["E_Z"], axis=1)
+    # ties / near-ties aside (none at this tolerance), identical
+    top2 = np.sort(ref["E_Z"], axis=1)[:, -2:, :]
+    clear = obs & ((top2[:, 1, :] - top2[:, 0, :]) > 1e-9)
+    assert np.array_equal(Zg[clear], want[clear]) and np.all(Zg[~obs] == NA)

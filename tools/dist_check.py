@@ -41,6 +41,25 @@ for (F, N, K, prec, iters) in [(300, 1000, 5, _lib.PREC_FP64, 12), (2048, 4096, 
               f"ELBO {np.max(np.abs(lb - lb1) / np.abs(lb1)):.2e}", flush=True)
         assert rel(W, W1) < 5e-6 and rel(Hall, H1) < 5e-6 and np.max(np.abs(lb - lb1) / np.abs(lb1)) < 5e-6
     dist.barrier()
+# column-sharded Gibbs: counter-based draws keyed by (f, global n, sweep) => the chain does not
+# depend on the sharding; E_W must be identical, E_H the matching block
+F, N, K = 200, 900, 8
+lo, hi = shard_columns(N, rank, world)
+e = Engine(device=local, n_global=N, n_offset=lo)
+e.generate_synthetic(F, hi - lo, 4, 0.7, 0.7, 31)
+e.set_allreduce_hook(make_allreduce_hook(dev))
+e.init_random_labels(K, 5)
+Wg, Hg, _, _ = e.gibbs_dirber(K, 1.0, 1.0, 0.5, iter=60, burnin=0.5, seed=13)
+e.close()
+if rank == 0:
+    e1 = Engine(device=local)
+    e1.generate_synthetic(F, N, 4, 0.7, 0.7, 31)
+    e1.init_random_labels(K, 5)
+    W1, H1, _, _ = e1.gibbs_dirber(K, 1.0, 1.0, 0.5, iter=60, burnin=0.5, seed=13)
+    e1.close()
+    print(f"sharded Gibbs world={world}: max|dE_W| {np.max(np.abs(Wg - W1)):.2e} max|dE_H block| {np.max(np.abs(Hg - H1[lo:hi])):.2e}", flush=True)
+    assert np.allclose(Wg, W1, rtol=0, atol=1e-12) and np.allclose(Hg, H1[lo:hi], rtol=0, atol=1e-12)
+dist.barrier()
 if rank == 0:
     print("dist_check ok")
 dist.destroy_process_group()
