@@ -34,7 +34,7 @@
 #include <cstdio>
 #include <cstdlib>
 
-#define TP_THREADS 384
+#define TP_THREADS 640
 #define TP_SPIN_LIMIT (1u << 20)
 
 // ---------------------------------------------------------------------------
@@ -495,7 +495,7 @@ struct TPCfg {
     static constexpr int SMEM_BYTES = STAGES * TILE_BYTES + 1024 /*align*/ + 512 /*barriers*/;
 };
 
-template <int KP, bool ROWS, bool WANT_LOG>
+template <int KP, bool ROWS, bool WANT_LOG, bool HAS_NA>
 __global__ void __launch_bounds__(TP_THREADS, 1)
 tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__ CUtensorMap tmLo, TPArgs a)
 {
@@ -520,7 +520,7 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
         for (int s = 0; s < C::STAGES; s++) { mbar_init(BAR_FULL(s), 1); mbar_init(BAR_EMPTY(s), 1); }
         for (int s = 0; s < C::NSLOT; s++) { mbar_init(BAR_SFULL + 8u * s, 1); mbar_init(BAR_RREADY + 8u * s, 128); }
         mbar_init(BAR_GFULL, 1);
-        mbar_init(BAR_UREADY, 256);
+        mbar_init(BAR_UREADY, 512);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -625,28 +625,34 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
         }
     } else if (warp >= 4) {
         // ===================== epilogue =====================
-        const int grp = (warp - 4) >> 2;            // handles steps t = grp (mod 2)
+        // four warpgroups, one per TMEM slot: group g handles steps t = g (mod 4).  More resident
+        // warps than strictly needed for throughput: the step latency (TMEM load -> select ->
+        // rcp -> pack -> TMEM store -> mbarrier) is what the MMA issuer otherwise waits on.
+        const int grp = (warp - 4) >> 2;            // = slot
         const int q = warp & 3;                     // TMEM lane quarter
         const int lrow = q * 32 + lane;             // owner lane within the tile
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-        uint32_t sf_phase = 0, g_phase = 0;         // sf_phase: bit per slot
+        const uint32_t t_s = tmem + lane_addr + C::COL_S + 64 * grp;
+        const uint32_t bar_sfull = BAR_SFULL + 8u * grp, bar_rready = BAR_RREADY + 8u * grp;
+        uint32_t sf_phase = 0, g_phase = 0;
         const float c0 = exp2f((float)(eU + eW - 14));
         const float finf = __int_as_float(0x7f800000);
         double log_acc_total = 0.0;
         bool first_item = true, ok = true;
         int64_t prev_w = -1;
+        constexpr int GCOLS = (KP == 128) ? 32 : 32;          // G columns drained per group
+        constexpr int NDRAIN = KP / GCOLS;                   // groups that take part (4 or 2)
         auto drain_G = [&](int64_t pw) {
-            const int pchunk = (int)(pw / a.owner_tiles);
-            const int64_t ptile = pw % a.owner_tiles;
-            float *dst = a.partial + (((int64_t)pchunk * a.owner_tiles + ptile) * 128 + lrow) * KP + grp * (KP / 2);
-#pragma unroll
-            for (int cc = 0; cc < KP / 64; cc++) {
+            if (grp < NDRAIN) {
+                const int pchunk = (int)(pw / a.owner_tiles);
+                const int64_t ptile = pw % a.owner_tiles;
+                float *dst = a.partial + (((int64_t)pchunk * a.owner_tiles + ptile) * 128 + lrow) * KP + grp * GCOLS;
                 uint32_t r[32];
-                tc_ld32(tmem + lane_addr + C::COL_G + grp * (KP / 2) + cc * 32, r);
+                tc_ld32(tmem + lane_addr + C::COL_G + grp * GCOLS, r);
                 tc_wait_ld();
 #pragma unroll
                 for (int i = 0; i < 32; i += 4)
-                    *reinterpret_cast<uint4 *>(dst + cc * 32 + i) = make_uint4(r[i], r[i + 1], r[i + 2], r[i + 3]);
+                    *reinterpret_cast<uint4 *>(dst + i) = make_uint4(r[i], r[i + 1], r[i + 2], r[i + 3]);
             }
         };
         for (int64_t w = blockIdx.x; w < n_items && ok; w += gridDim.x) {
@@ -663,27 +669,23 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
                 tc_fence_after();
                 drain_G(prev_w);
             }
-            // ---- owner operand of this item -> TMEM (each group writes half of the k range)
-            {
-                const __half *src = a.U_hi + l * KP + grp * (KP / 2);
-                const uint32_t ucol = tmem + lane_addr + C::COL_U + grp * (KP / 4);
+            // ---- owner operand of this item -> TMEM: 32 f16 (16 columns) per participating group
+            if (grp < KP / 32) {
+                const __half *src = a.U_hi + l * KP + grp * 32;
+                uint32_t r[16];
 #pragma unroll
-                for (int cc = 0; cc < KP / 64; cc++) {
-                    uint32_t r[16];
-#pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        uint4 v = lane_ok ? __ldg(reinterpret_cast<const uint4 *>(src + cc * 32) + i) : make_uint4(0, 0, 0, 0);
-                        r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
-                    }
-                    tc_st16(ucol + cc * 16, r);
+                for (int i = 0; i < 4; i++) {
+                    uint4 v = lane_ok ? __ldg(reinterpret_cast<const uint4 *>(src) + i) : make_uint4(0, 0, 0, 0);
+                    r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
                 }
+                tc_st16(tmem + lane_addr + C::COL_U + grp * 16, r);
                 tc_wait_st();
-                tc_fence_before();
-                mbar_arrive(BAR_UREADY);
             }
+            tc_fence_before();
+            mbar_arrive(BAR_UREADY);
             first_item = false;
             prev_w = w;
-            // ---- steps t = grp, grp+2, ...
+            // ---- steps t = grp, grp+4, ...
             float log_acc = 0.f;
             const int64_t orow = ROWS ? l : (l >> 1);
             const uint32_t bsel = ROWS ? 0u : (uint32_t)(l & 1);
@@ -697,47 +699,42 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
 #pragma unroll
                 for (int i = 0; i < WPS; i++) {
                     bv[i] = lane_ok ? __ldg(vrow + wi + i) : 0u;
-                    bm[i] = lane_ok ? __ldg(mrow + wi + i) : 0u;
+                    bm[i] = HAS_NA ? (lane_ok ? __ldg(mrow + wi + i) : 0u) : 0xffffffffu;
                 }
             };
             if (grp < nst) load_bits(grp);
-            for (int t = grp; t < nst && ok; t += 2) {
-                const int slot = t & 3;
-                const uint32_t t_s = tmem + lane_addr + C::COL_S + 64 * slot;
+            for (int t = grp; t < nst && ok; t += 4) {
                 uint32_t sel[WPS], vv[WPS];
 #pragma unroll
                 for (int i = 0; i < WPS; i++) {
                     vv[i] = bv[i];
                     sel[i] = ROWS ? bm[i] : ((bsel ? bv[i] : ~bv[i]) & bm[i]);
                 }
-                if (t + 2 < nst) load_bits(t + 2);
-                ok = ok && mbar_wait(BAR_SFULL + 8u * slot, (sf_phase >> slot) & 1u, abort_flag, 8);
-                sf_phase ^= 1u << slot;
+                if (t + 4 < nst) load_bits(t + 4);
+                ok = ok && mbar_wait(bar_sfull, sf_phase, abort_flag, 8);
+                sf_phase ^= 1;
                 tc_fence_after();
-                uint32_t s0[32], s1[32];
-                tc_ld32(t_s, s0);
-                tc_ld32(t_s + 32, s1);
-                tc_wait_ld();
-                if (a.dbg != nullptr && w == 0 && t < 4) {
-                    for (int i = 0; i < 32; i++) {
-                        a.dbg[(lrow * 256) + t * 64 + i] = __uint_as_float(s0[i]);
-                        a.dbg[(lrow * 256) + t * 64 + 32 + i] = __uint_as_float(s1[i]);
-                    }
-                }
 #pragma unroll
                 for (int cc = 0; cc < 2; cc++) {
-                    uint32_t (&s)[32] = cc ? s1 : s0;
-                    uint32_t rp[16];
+                    uint32_t s[32], rp[16];
+                    tc_ld32(t_s + cc * 32, s);
+                    tc_wait_ld();
+                    if (a.dbg != nullptr && w == 0 && t < 4) {
+                        for (int i = 0; i < 32; i++) a.dbg[(lrow * 256) + t * 64 + cc * 32 + i] = __uint_as_float(s[i]);
+                    }
                     if (ROWS) {
                         // 32 columns = 16 entries (n) x 2 branches, column 2j+b
                         const uint32_t m16 = sel[0] >> (cc * 16);
                         const uint32_t v16 = vv[0] >> (cc * 16);
 #pragma unroll
                         for (int j = 0; j < 16; j++) {
-                            const bool vb = (v16 >> j) & 1u, mb = (m16 >> j) & 1u;
+                            const bool vb = (v16 >> j) & 1u;
                             float sv = __uint_as_float(vb ? s[2 * j + 1] : s[2 * j]);
-                            if (WANT_LOG) log_acc += mb ? fast_lg2(sv) : 0.f;
-                            sv = mb ? sv : finf;                     // masked entry: R = 0
+                            if (HAS_NA) {
+                                const bool mb = (m16 >> j) & 1u;
+                                if (WANT_LOG) log_acc += mb ? fast_lg2(sv) : 0.f;
+                                sv = mb ? sv : finf;                 // masked entry: R = 0
+                            } else if (WANT_LOG) log_acc += fast_lg2(sv);
                             const float r = c0 * fast_rcp(sv);
                             rp[j] = pack_h2_sat(vb ? 0.f : r, vb ? r : 0.f);
                         }
@@ -754,7 +751,7 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
                 }
                 tc_wait_st();
                 tc_fence_before();
-                mbar_arrive(BAR_RREADY + 8u * slot);
+                mbar_arrive(bar_rready);
             }
             if (WANT_LOG) log_acc_total += (double)log_acc;
         }
@@ -796,14 +793,19 @@ __global__ void tp_logfix_kernel(const double *dacc, const int *dexp, double nse
         *sumlogD += 0.6931471805599453 * (dacc[0] - nsel * (double)(dexp[0] + dexp[1]));
 }
 
-template <int KP, bool ROWS, bool WANT_LOG>
-static cudaError_t launch_tp(const CUtensorMap &tm, const CUtensorMap &tmlo, const TPArgs &a, int grid, cudaStream_t st)
+template <int KP, bool ROWS, bool WANT_LOG, bool HAS_NA>
+static cudaError_t launch_tp2(const CUtensorMap &tm, const CUtensorMap &tmlo, const TPArgs &a, int grid, cudaStream_t st)
 {
-    cudaError_t e = cudaFuncSetAttribute(tp_pass_kernel<KP, ROWS, WANT_LOG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(tp_pass_kernel<KP, ROWS, WANT_LOG, HAS_NA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          TPCfg<KP>::SMEM_BYTES);
     if (e != cudaSuccess) return e;
-    tp_pass_kernel<KP, ROWS, WANT_LOG><<<grid, TP_THREADS, TPCfg<KP>::SMEM_BYTES, st>>>(tm, tmlo, a);
+    tp_pass_kernel<KP, ROWS, WANT_LOG, HAS_NA><<<grid, TP_THREADS, TPCfg<KP>::SMEM_BYTES, st>>>(tm, tmlo, a);
     return cudaGetLastError();
+}
+template <int KP, bool ROWS, bool WANT_LOG>
+static cudaError_t launch_tp(const CUtensorMap &tm, const CUtensorMap &tmlo, const TPArgs &a, int grid, cudaStream_t st, bool has_na)
+{
+    return has_na ? launch_tp2<KP, ROWS, WANT_LOG, true>(tm, tmlo, a, grid, st) : launch_tp2<KP, ROWS, WANT_LOG, false>(tm, tmlo, a, grid, st);
 }
 
 static float *g_tp_dbg = nullptr; // set by nbmf_debug_tp_dump only
@@ -845,15 +847,18 @@ int tp_pass(nbmf_handle *h, int owner_rows, double *sumlogD)
     if (a.want_log) cudaMemsetAsync(s->dacc, 0, 16, h->stream);
     const int64_t items = (int64_t)a.n_chunks * a.owner_tiles;
     const int grid = (int)std::min<int64_t>(items, h->sm_count);
+    // the mask plane is skipped only when there is no NA and no padding anywhere (padded lanes /
+    // streamed rows rely on the mask bits being zero)
+    const bool use_mask = h->has_na || (h->F % 128 != 0) || (h->N % 64 != 0);
     cudaError_t e;
     if (KP == 128) {
-        if (!owner_rows) e = launch_tp<128, false, false>(s->tmA, s->tmAlo, a, grid, h->stream);
-        else if (a.want_log) e = launch_tp<128, true, true>(s->tmB, s->tmBlo, a, grid, h->stream);
-        else e = launch_tp<128, true, false>(s->tmB, s->tmBlo, a, grid, h->stream);
+        if (!owner_rows) e = launch_tp<128, false, false>(s->tmA, s->tmAlo, a, grid, h->stream, use_mask);
+        else if (a.want_log) e = launch_tp<128, true, true>(s->tmB, s->tmBlo, a, grid, h->stream, use_mask);
+        else e = launch_tp<128, true, false>(s->tmB, s->tmBlo, a, grid, h->stream, use_mask);
     } else {
-        if (!owner_rows) e = launch_tp<64, false, false>(s->tmA, s->tmAlo, a, grid, h->stream);
-        else if (a.want_log) e = launch_tp<64, true, true>(s->tmB, s->tmBlo, a, grid, h->stream);
-        else e = launch_tp<64, true, false>(s->tmB, s->tmBlo, a, grid, h->stream);
+        if (!owner_rows) e = launch_tp<64, false, false>(s->tmA, s->tmAlo, a, grid, h->stream, use_mask);
+        else if (a.want_log) e = launch_tp<64, true, true>(s->tmB, s->tmBlo, a, grid, h->stream, use_mask);
+        else e = launch_tp<64, true, false>(s->tmB, s->tmBlo, a, grid, h->stream, use_mask);
     }
     if (e != cudaSuccess) { h->err = std::string("tp_pass launch: ") + cudaGetErrorString(e); return NBMF_ERR_CUDA; }
     tp_reduce_kernel<<<(unsigned)((a.L * KP + 255) / 256), 256, 0, h->stream>>>(s->partial, a.n_chunks, Lpad, a.L, KP, s->dexp,
