@@ -151,7 +151,7 @@ int tp_prepare(nbmf_handle *h)
     if (rc) return rc;
     rc = make_map(h, &s->tmBlo, s->B_lo, s->N2pad, KP);
     if (rc) return rc;
-    s->chunk_steps = h->opts.flush_interval > 0 ? h->opts.flush_interval : 128;
+    s->chunk_steps = h->opts.flush_interval > 0 ? h->opts.flush_interval : 512;
     const char *env = getenv("NBMF_TP_CHUNK_STEPS");
     if (env && atoi(env) > 0) s->chunk_steps = atoi(env);
     return NBMF_OK;
@@ -662,6 +662,17 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
             const int nst = (int)min((int64_t)a.chunk_steps, a.stream_steps - t0);
             const int64_t l = tile * 128 + lrow;
             const bool lane_ok = l < a.L;
+            // ---- owner operand of this item: issue the global loads before waiting for the
+            //      previous item's accumulator, so their latency overlaps its last MMAs
+            uint32_t ur[16];
+            if (grp < KP / 32) {
+                const __half *src = a.U_hi + l * KP + grp * 32;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    uint4 v = lane_ok ? __ldg(reinterpret_cast<const uint4 *>(src) + i) : make_uint4(0, 0, 0, 0);
+                    ur[4 * i] = v.x; ur[4 * i + 1] = v.y; ur[4 * i + 2] = v.z; ur[4 * i + 3] = v.w;
+                }
+            }
             // ---- drain G of the previous item
             if (!first_item) {
                 ok = ok && mbar_wait(BAR_GFULL, g_phase, abort_flag, 7);
@@ -669,16 +680,8 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
                 tc_fence_after();
                 drain_G(prev_w);
             }
-            // ---- owner operand of this item -> TMEM: 32 f16 (16 columns) per participating group
             if (grp < KP / 32) {
-                const __half *src = a.U_hi + l * KP + grp * 32;
-                uint32_t r[16];
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    uint4 v = lane_ok ? __ldg(reinterpret_cast<const uint4 *>(src) + i) : make_uint4(0, 0, 0, 0);
-                    r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
-                }
-                tc_st16(tmem + lane_addr + C::COL_U + grp * 16, r);
+                tc_st16(tmem + lane_addr + C::COL_U + grp * 16, ur);
                 tc_wait_st();
             }
             tc_fence_before();
@@ -826,7 +829,14 @@ int tp_pass(nbmf_handle *h, int owner_rows, double *sumlogD)
     }
     a.owner_tiles = (a.L + 127) / 128;
     a.stream_steps = (S_rows + 63) / 64;
-    a.chunk_steps = (int)std::min<int64_t>(s->chunk_steps, a.stream_steps);
+    // chunk length: long chunks amortise the per-item drain / operand reload (C5: 64 -> 167 ms,
+    // 128 -> 154, 512 -> 141 ms per iteration), but there must be enough items for every SM
+    {
+        const int64_t min_chunks = std::max<int64_t>(1, (4 * (int64_t)h->sm_count + a.owner_tiles - 1) / a.owner_tiles);
+        int64_t cs = (a.stream_steps + min_chunks - 1) / min_chunks;
+        cs = std::max<int64_t>(std::min<int64_t>(cs, s->chunk_steps), std::min<int64_t>(16, a.stream_steps));
+        a.chunk_steps = (int)std::min<int64_t>(cs, a.stream_steps);
+    }
     a.n_chunks = (int)((a.stream_steps + a.chunk_steps - 1) / a.chunk_steps);
     const int64_t Lpad = a.owner_tiles * 128;
     size_t need = (size_t)a.n_chunks * Lpad * KP * 4;
