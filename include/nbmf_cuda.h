@@ -47,8 +47,10 @@ typedef enum nbmf_status {
 typedef enum nbmf_precision {
     NBMF_PREC_AUTO = 0,        /* FP64 FMA path for K < 32, tensor path otherwise        */
     NBMF_PREC_FP64 = 1,        /* FP64 FMA + warp shuffles (any K <= 512)                 */
-    NBMF_PREC_TENSOR = 2,      /* tcgen05 f16 hi/lo split, fp32 accumulate in TMEM        */
-    NBMF_PREC_TENSOR_FULL = 3  /* tensor path, every operand split (3+2 passes)           */
+    NBMF_PREC_TENSOR = 2,      /* tcgen05 f16: stage 2 with the streamed operand split hi+lo,
+                                  fp32 accumulate in TMEM (1e-5 parity at every size tested) */
+    NBMF_PREC_TENSOR_FAST = 3  /* same, hi only in stage 2: 1/3 fewer MMAs; its error falls
+                                  like ~1/sqrt(min(F,N)) -- see DESIGN.md before using it   */
 } nbmf_precision;
 
 /* VB_DirBer_Rcpp modes */

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(HERE, "libnbmf_cuda.so")
 
 NBMF_OK = 0
-PREC_AUTO, PREC_FP64, PREC_TENSOR, PREC_TENSOR_FULL = 0, 1, 2, 3
+PREC_AUTO, PREC_FP64, PREC_TENSOR, PREC_TENSOR_FAST = 0, 1, 2, 3
 DIRBER_EXACT_WAVEFRONT, DIRBER_CONTRACTION = 0, 1
 
 

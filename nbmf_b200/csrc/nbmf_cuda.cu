@@ -466,7 +466,7 @@ static bool use_tensor_path(const nbmf_handle *h)
 {
     int p = h->opts.precision;
     if (p == NBMF_PREC_FP64) return false;
-    if (p == NBMF_PREC_TENSOR || p == NBMF_PREC_TENSOR_FULL) return true;
+    if (p == NBMF_PREC_TENSOR || p == NBMF_PREC_TENSOR_FAST) return true;
     return tp_supported(h); // AUTO
 }
 

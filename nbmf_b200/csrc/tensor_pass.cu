@@ -472,6 +472,7 @@ struct TPArgs {
     int want_log;
     float *dbg;                    // optional debug dump
     int dbg_flags;                 // timing experiments only: 1 = skip lo TMA, 2 = skip all TMA
+    int use_lo;                    // stage 2 adds the W_lo term (NBMF_PREC_TENSOR); 0 = hi only (NBMF_PREC_TENSOR_FAST)
 };
 
 // One step = 64 streamed rows.  Shared-memory stage: [hi: KB blocks][lo: KB blocks], each
@@ -549,7 +550,7 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
                     const uint32_t dst = smem_base + stage * C::TILE_BYTES;
                     const int row0 = (int)((t0 + t) * C::STEP_ROWS);
                     if (a.dbg_flags & 2) { mbar_arrive(BAR_FULL(stage)); }
-                    else if (a.dbg_flags & 1) {
+                    else if ((a.dbg_flags & 1) || !a.use_lo) {
                         mbar_expect_tx(BAR_FULL(stage), C::PART_BYTES);
                         for (int kb = 0; kb < C::KB; kb++) tma_load_2d(dst + kb * C::BLOCK_BYTES, &tmHi, kb * 64, row0, BAR_FULL(stage));
                     } else {
@@ -610,11 +611,14 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
                     const uint32_t lo = (((smem_base + g_stage * C::TILE_BYTES) >> 4) & 0x3FFFu) | DLO2;
                     const uint32_t rcol = tmem + C::COL_S + 64 * slot;
 #pragma unroll
-                    for (int p = 0; p < 2; p++)
+                    for (int j = 0; j < C::STEP_ROWS / 16; j++)
+                        tc_mma_ts2(tmem + C::COL_G, rcol + j * 8, lo + ((j * (16 * 128)) >> 4), DHI, IDESC2,
+                                   (t == 0 && j == 0) ? 0u : 1u);
+                    if (a.use_lo) {
 #pragma unroll
                         for (int j = 0; j < C::STEP_ROWS / 16; j++)
-                            tc_mma_ts2(tmem + C::COL_G, rcol + j * 8, lo + ((p * C::PART_BYTES + j * (16 * 128)) >> 4), DHI,
-                                       IDESC2, (t == 0 && p == 0 && j == 0) ? 0u : 1u);
+                            tc_mma_ts2(tmem + C::COL_G, rcol + j * 8, lo + ((C::PART_BYTES + j * (16 * 128)) >> 4), DHI, IDESC2, 1u);
+                    }
                     tc_commit(BAR_EMPTY(g_stage));   // tile t fully consumed
                     if (++g_stage == C::STAGES) g_stage = 0;
                     if (t + C::NSLOT < nst) stage1(t + C::NSLOT);
@@ -636,6 +640,7 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
         const uint32_t bar_sfull = BAR_SFULL + 8u * grp, bar_rready = BAR_RREADY + 8u * grp;
         uint32_t sf_phase = 0, g_phase = 0;
         const float c0 = exp2f((float)(eU + eW - 14));
+        const float c1 = exp2f((float)(-(eU + eW)));   // S * c1 = D: lg2.approx's relative error must apply to log2 D, not to log2 S
         const float finf = __int_as_float(0x7f800000);
         double log_acc_total = 0.0;
         bool first_item = true, ok = true;
@@ -735,9 +740,9 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
                             float sv = __uint_as_float(vb ? s[2 * j + 1] : s[2 * j]);
                             if (HAS_NA) {
                                 const bool mb = (m16 >> j) & 1u;
-                                if (WANT_LOG) log_acc += mb ? fast_lg2(sv) : 0.f;
+                                if (WANT_LOG) log_acc += mb ? fast_lg2(sv * c1) : 0.f;
                                 sv = mb ? sv : finf;                 // masked entry: R = 0
-                            } else if (WANT_LOG) log_acc += fast_lg2(sv);
+                            } else if (WANT_LOG) log_acc += fast_lg2(sv * c1);
                             const float r = c0 * fast_rcp(sv);
                             rp[j] = pack_h2_sat(vb ? 0.f : r, vb ? r : 0.f);
                         }
@@ -789,11 +794,11 @@ __global__ void tp_reduce_kernel(const float *__restrict__ partial, int n_chunks
     G[i] = ldexp(s, 14 - dexp[which_w]);
 }
 
-// sumlogD += ln2 * (sum log2 S - nsel * (eA + eB))
+// sumlogD += ln2 * sum log2 D
 __global__ void tp_logfix_kernel(const double *dacc, const int *dexp, double nsel, double *sumlogD)
 {
     if (threadIdx.x == 0 && blockIdx.x == 0)
-        *sumlogD += 0.6931471805599453 * (dacc[0] - nsel * (double)(dexp[0] + dexp[1]));
+        *sumlogD += 0.6931471805599453 * dacc[0];
 }
 
 template <int KP, bool ROWS, bool WANT_LOG, bool HAS_NA>
@@ -852,6 +857,7 @@ int tp_pass(nbmf_handle *h, int owner_rows, double *sumlogD)
     a.partial = s->partial;
     a.dexp = s->dexp; a.dacc = s->dacc; a.derr = s->derr;
     a.want_log = (sumlogD != nullptr);
+    a.use_lo = (h->opts.precision != NBMF_PREC_TENSOR_FAST);
     a.dbg = g_tp_dbg;
     { const char *f = getenv("NBMF_TP_DEBUG_FLAGS"); a.dbg_flags = f ? atoi(f) : 0; }
     if (a.want_log) cudaMemsetAsync(s->dacc, 0, 16, h->stream);

@@ -73,6 +73,24 @@ def test_tensor_path_matches_fp64_path(F, N, K, na, iters, gamma):
     assert np.allclose(Wt.sum(1), 1.0, atol=1e-12)
 
 
+def test_tensor_single_update_and_fast_mode():
+    """One update from identical statistics: the injected error per update is ~1e-6 or below; the
+    opt-in hi-only mode (NBMF_PREC_TENSOR_FAST) stays within 1e-5 at this size."""
+    from nbmf_b200 import Engine, _lib
+    F = N = 4096; K = 128
+    res = {}
+    for prec in (_lib.PREC_FP64, _lib.PREC_TENSOR, _lib.PREC_TENSOR_FAST):
+        e = Engine(precision=prec)
+        e.generate_synthetic(F, N, 8, 1.0, 1.0, 5)
+        e.init_random_labels(K, 6)
+        e.vb_aspect(K, 1.0, 1.0, 1.0 / K, iter=3, checklb=True)
+        res[prec] = e.get_stats(K)
+        e.close()
+    for prec, tol in ((_lib.PREC_TENSOR, 2e-6), (_lib.PREC_TENSOR_FAST, 1e-5)):
+        for a, b in zip(res[prec], res[_lib.PREC_FP64]):
+            assert relF(a, b) < tol, (prec, relF(a, b))
+
+
 def test_auto_precision_selects_tensor_path_for_large_k():
     from nbmf_b200 import Engine, _lib
     e = Engine(precision=_lib.PREC_AUTO)
