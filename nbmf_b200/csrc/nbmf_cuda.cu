@@ -15,6 +15,17 @@
 
 static inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
 
+// device allocation that is released on every return path
+template <class T> struct DevBuf {
+    T *p = nullptr;
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t count) { return cudaMalloc((void **)&p, (count ? count : 1) * sizeof(T)); }
+    operator T *() const { return p; }
+};
+
 static int fail(nbmf_handle *h, int code, const char *msg)
 {
     if (h) h->err = msg;
@@ -281,9 +292,9 @@ extern "C" int nbmf_generate_synthetic(nbmf_handle *h, int64_t F, int64_t N, int
         return fail(h, NBMF_ERR_ARG, "nbmf_generate_synthetic: bad arguments (Ktrue <= 16)");
     int rc = alloc_planes(h, F, N);
     if (rc) return rc;
-    float *Wt = nullptr, *Ht = nullptr;
-    CK(cudaMalloc(&Wt, (size_t)F * Ktrue * 4));
-    CK(cudaMalloc(&Ht, (size_t)N * Ktrue * 4));
+    DevBuf<float> Wt, Ht;
+    CK(Wt.alloc((size_t)F * Ktrue));
+    CK(Ht.alloc((size_t)N * Ktrue));
     unsigned long long *cnt = (unsigned long long *)h->scal + SC_TMP;
     CK(cudaMemsetAsync(cnt, 0, 16, h->stream));
     synth_W_kernel<<<nblk(F, 256), 256, 0, h->stream>>>(F, Ktrue, a, seed, Wt);
@@ -299,7 +310,6 @@ extern "C" int nbmf_generate_synthetic(nbmf_handle *h, int64_t F, int64_t N, int
     h->nobs = F * N;
     rc = build_row_planes(h);
     CK(cudaStreamSynchronize(h->stream));
-    cudaFree(Wt); cudaFree(Ht);
     return rc;
 }
 
@@ -964,10 +974,10 @@ extern "C" int nbmf_gibbs_sweep_given_W(nbmf_handle *h, const int32_t *v_n, cons
     if (!h) return NBMF_ERR_ARG;
     if (!v_n || !W || !C_mean || F <= 0 || K <= 0 || K > 1024) return fail(h, NBMF_ERR_ARG, "bad arguments");
     CK(cudaSetDevice(h->device));
-    int32_t *dv = nullptr, *lab = nullptr;
-    double *dW = nullptr, *dC = nullptr;
-    CK(cudaMalloc(&dv, (size_t)F * 4)); CK(cudaMalloc(&lab, (size_t)F * 4));
-    CK(cudaMalloc(&dW, (size_t)F * K * 8)); CK(cudaMalloc(&dC, (size_t)F * K * 8));
+    DevBuf<int32_t> dv, lab;
+    DevBuf<double> dW, dC;
+    CK(dv.alloc((size_t)F)); CK(lab.alloc((size_t)F));
+    CK(dW.alloc((size_t)F * K)); CK(dC.alloc((size_t)F * K));
     CK(cudaMemcpyAsync(dv, v_n, (size_t)F * 4, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(dW, W, (size_t)F * K * 8, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemsetAsync(dC, 0, (size_t)F * K * 8, h->stream));
@@ -975,7 +985,6 @@ extern "C" int nbmf_gibbs_sweep_given_W(nbmf_handle *h, const int32_t *v_n, cons
     LAUNCH_CHECK();
     CK(cudaMemcpyAsync(C_mean, dC, (size_t)F * K * 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    cudaFree(dv); cudaFree(lab); cudaFree(dW); cudaFree(dC);
     return NBMF_OK;
 }
 
@@ -988,12 +997,12 @@ extern "C" int nbmf_predictive_ll(nbmf_handle *h, const double *E_W, const doubl
     if (!h) return NBMF_ERR_ARG;
     if (!E_W || !E_H || !Vt || F <= 0 || N <= 0 || K <= 0) return fail(h, NBMF_ERR_ARG, "bad arguments");
     CK(cudaSetDevice(h->device));
-    double *dW = nullptr, *dH = nullptr, *stg = nullptr, *dll = nullptr;
-    int32_t *dV = nullptr;
+    DevBuf<double> dW, dH, stg, dll;
+    DevBuf<int32_t> dV;
     int64_t cols_per = std::min<int64_t>(N, std::max<int64_t>(1, (int64_t)(256ll << 20) / (F * 4)));
-    CK(cudaMalloc(&dW, (size_t)F * K * 8)); CK(cudaMalloc(&dH, (size_t)N * K * 8));
-    CK(cudaMalloc(&stg, (size_t)std::max(F, N) * K * 8)); CK(cudaMalloc(&dll, 16));
-    CK(cudaMalloc(&dV, (size_t)cols_per * F * 4));
+    CK(dW.alloc((size_t)F * K)); CK(dH.alloc((size_t)N * K));
+    CK(stg.alloc((size_t)std::max(F, N) * K)); CK(dll.alloc(2));
+    CK(dV.alloc((size_t)cols_per * F));
     CK(cudaMemsetAsync(dll, 0, 16, h->stream));
     CK(cudaMemcpyAsync(stg, E_W, (size_t)F * K * 8, cudaMemcpyHostToDevice, h->stream));
     colmajor_to_rows_kernel<<<nblk(F * K, 256), 256, 0, h->stream>>>(stg, F, K, dW, K, 1, 0);
@@ -1004,7 +1013,7 @@ extern "C" int nbmf_predictive_ll(nbmf_handle *h, const double *E_W, const doubl
     for (int64_t n0 = 0; n0 < N; n0 += cols_per) {
         int64_t nc = std::min(cols_per, N - n0);
         CK(cudaMemcpyAsync(dV, Vt + n0 * F, (size_t)nc * F * 4, cudaMemcpyHostToDevice, h->stream));
-        predictive_ll_kernel<<<nblk(nc * F, 256), 256, 0, h->stream>>>(dV, F, nc, n0, K, K, dW, dH, dll, (unsigned long long *)(dll + 1));
+        predictive_ll_kernel<<<nblk(nc * F, 256), 256, 0, h->stream>>>(dV, F, nc, n0, K, K, dW, dH, dll, (unsigned long long *)(dll.p + 1));
         LAUNCH_CHECK();
         CK(cudaStreamSynchronize(h->stream));
     }
@@ -1012,6 +1021,5 @@ extern "C" int nbmf_predictive_ll(nbmf_handle *h, const double *E_W, const doubl
     CK(cudaMemcpy(out, dll, 16, cudaMemcpyDeviceToHost));
     if (ll) *ll = out[0];
     if (n_test) { unsigned long long c; memcpy(&c, &out[1], 8); *n_test = (int64_t)c; }
-    cudaFree(dW); cudaFree(dH); cudaFree(stg); cudaFree(dll); cudaFree(dV);
     return NBMF_OK;
 }
