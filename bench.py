@@ -273,7 +273,8 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "iters_per_s": args.steps / (ms * 1e-3),
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                "dtype": "f64" if (args.precision == 1 or (args.precision == 0 and K < 32)) else "f16x2-split/f32-accum",
+                "dtype": {0: "f64", 1: "f16 (streamed operand hi+lo in stage 2) / f32 accumulate in TMEM",
+                          2: "f16 (hi only; validated at this size, profiles/r1_error_growth_c5.log) / f32 accumulate in TMEM"}[int(tim["path"])],
                 "data": "synthetic",
                 "config": {"workload": wl["desc"], "F": F, "N": N, "K": K, "columns_per_rank": Nl,
                            "l2_policy": "inputs larger than L2 (bit planes + operands stream from HBM)"

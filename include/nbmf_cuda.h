@@ -45,7 +45,8 @@ typedef enum nbmf_status {
 
 /* which arithmetic the contraction kernel uses */
 typedef enum nbmf_precision {
-    NBMF_PREC_AUTO = 0,        /* FP64 FMA path for K < 32, tensor path otherwise        */
+    NBMF_PREC_AUTO = 0,        /* FP64 FMA path for K <= 32 or small F,N; tensor path otherwise,
+                                  hi-only stage 2 once min(F, N) >= 131072  */
     NBMF_PREC_FP64 = 1,        /* FP64 FMA + warp shuffles (any K <= 512)                 */
     NBMF_PREC_TENSOR = 2,      /* tcgen05 f16: stage 2 with the streamed operand split hi+lo,
                                   fp32 accumulate in TMEM (1e-5 parity at every size tested) */
@@ -85,6 +86,7 @@ typedef struct nbmf_timing {
     double exchange_ms;
     int64_t launches;       /* kernels launched inside the loop              */
     int64_t iters;
+    int64_t path;           /* contraction used: 0 FP64 FMA, 1 tensor (hi+lo stage 2), 2 tensor (hi only) */
 } nbmf_timing;
 
 const char *nbmf_version(void);

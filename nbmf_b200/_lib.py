@@ -25,7 +25,7 @@ class NbmfOpts(C.Structure):
 class NbmfTiming(C.Structure):
     _fields_ = [("total_ms", C.c_double), ("params_ms", C.c_double), ("pass_rows_ms", C.c_double),
                 ("pass_cols_ms", C.c_double), ("exchange_ms", C.c_double), ("launches", C.c_int64),
-                ("iters", C.c_int64)]
+                ("iters", C.c_int64), ("path", C.c_int64)]
 
 
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)

@@ -857,7 +857,16 @@ int tp_pass(nbmf_handle *h, int owner_rows, double *sumlogD)
     a.partial = s->partial;
     a.dexp = s->dexp; a.dacc = s->dacc; a.derr = s->derr;
     a.want_log = (sumlogD != nullptr);
-    a.use_lo = (h->opts.precision != NBMF_PREC_TENSOR_FAST);
+    // AUTO: the W_lo term of stage 2 buys ~5x accuracy at 10^3..10^4 rows/columns, but its benefit
+    // falls like 1/sqrt(reduction length): at 262144^2 hi-only is within 1.6x of hi+lo and both are
+    // ~1e-6 of the FP64 path (profiles/r1_error_growth_c5.log), so it is dropped there.
+    {
+        const int64_t n_glob = h->opts.n_global > 0 ? h->opts.n_global : h->N;
+        if (h->opts.precision == NBMF_PREC_TENSOR) a.use_lo = 1;
+        else if (h->opts.precision == NBMF_PREC_TENSOR_FAST) a.use_lo = 0;
+        else a.use_lo = (std::min<int64_t>(h->F, n_glob) < 131072) ? 1 : 0;
+        h->timing.path = a.use_lo ? 1 : 2;
+    }
     a.dbg = g_tp_dbg;
     { const char *f = getenv("NBMF_TP_DEBUG_FLAGS"); a.dbg_flags = f ? atoi(f) : 0; }
     if (a.want_log) cudaMemsetAsync(s->dacc, 0, 16, h->stream);

@@ -352,3 +352,26 @@ def test_argmax_labels_hand_off_matches_which_max():
     top2 = np.sort(ref["E_Z"], axis=1)[:, -2:, :]
     clear = obs & ((top2[:, 1, :] - top2[:, 0, :]) > 1e-9)
     assert np.array_equal(Zg[clear], want[clear]) and np.all(Zg[~obs] == NA)
+
+
+def test_allreduce_hook_plumbing_single_rank():
+    """The exchange hook is called once per iteration with the F x Kp device buffer (plus once per
+    label initialisation); a sum over a world of one leaves the results unchanged, and the ELBO
+    terms split into local (sum log D, column prior) and replicated (row prior) parts."""
+    from nbmf_b200 import Engine
+    from nbmf_b200.dist import combine_lowerbounds
+    V = make_problem(70, 90, 3, 21, 0.1)
+    K = 5
+    Z = oracle.random_labels(V, K, 2)
+    calls = []
+    e = Engine(n_global=90, n_offset=0); e.set_data(V)
+    e.set_allreduce_hook(lambda ptr, count, stream: calls.append((ptr != 0, count, stream != 0)))
+    e.init_from_labels(Z, K)
+    W, H, lb, _ = e.vb_aspect(K, 1.0, 1.0, 0.5, iter=7, checklb=True)
+    terms = e.vb_lb_terms(7)
+    e.close()
+    assert len(calls) == 1 + 7 and all(c[0] and c[2] for c in calls) and all(c[1] >= 70 * K for c in calls)
+    ref = oracle.vb_aspect(V, Z, K, 1.0, 1.0, 0.5, iter=7, checklb=True)
+    assert relF(W, ref["E_W"]) < 1e-9 and relF(H, ref["E_H"]) < 1e-9
+    assert np.allclose(combine_lowerbounds(terms, lambda x: x), lb, rtol=1e-14)
+    assert np.max(np.abs(lb - ref["lowerbounds"]) / np.abs(ref["lowerbounds"])) < 1e-10
