@@ -375,3 +375,27 @@ def test_allreduce_hook_plumbing_single_rank():
     assert relF(W, ref["E_W"]) < 1e-9 and relF(H, ref["E_H"]) < 1e-9
     assert np.allclose(combine_lowerbounds(terms, lambda x: x), lb, rtol=1e-14)
     assert np.max(np.abs(lb - ref["lowerbounds"]) / np.abs(ref["lowerbounds"])) < 1e-10
+
+
+def test_degenerate_inputs():
+    """All entries NA; a single observed entry; K=1."""
+    from nbmf_b200 import Engine, VB_Aspect_Rcpp, VB_DirBer_Rcpp
+    V = np.full((5, 6), NA, dtype=np.int32, order="F")
+    Z = np.full((5, 6), NA, dtype=np.int32, order="F")
+    r = VB_Aspect_Rcpp(V, Z, 3, iter=3, checklb=True)
+    o = oracle.vb_aspect(V, Z, 3, iter=3, checklb=True)
+    assert np.allclose(r["E_W"], 1 / 3) and np.allclose(r["E_H"], 0.5)
+    assert np.allclose(r["lowerbounds"], o["lowerbounds"], rtol=1e-12, atol=1e-12)
+    V[2, 4] = 1; Z[2, 4] = 0
+    r = VB_Aspect_Rcpp(V, Z, 3, iter=4, checklb=True)
+    o = oracle.vb_aspect(V, Z, 3, iter=4, checklb=True)
+    assert relF(r["E_W"], o["E_W"]) < 1e-12 and relF(r["E_H"], o["E_H"]) < 1e-12
+    d = VB_DirBer_Rcpp(V, Z, 2, iter=3)
+    od = oracle.vb_dirber(V, Z, 2, iter=3)
+    assert np.array_equal(d["E_W"], od["E_W"], equal_nan=True) and np.array_equal(d["E_H"], od["E_H"], equal_nan=True)
+    V2 = make_problem(9, 11, 2, 3)
+    Z2 = oracle.random_labels(V2, 1, 1)
+    r = VB_Aspect_Rcpp(V2, Z2, 1, iter=3, checklb=True)
+    o = oracle.vb_aspect(V2, Z2, 1, iter=3, checklb=True)
+    assert np.allclose(r["E_W"], 1.0) and relF(r["E_H"], o["E_H"]) < 1e-12
+    assert np.allclose(r["lowerbounds"], o["lowerbounds"], rtol=1e-12)

@@ -125,3 +125,30 @@ def test_tensor_path_contraction_mode_dirber():
         outs.append(e.vb_dirber(K, 1.0, 1.0, 1.0, iter=6, mode=_lib.DIRBER_CONTRACTION))
         e.close()
     assert relF(outs[1][0], outs[0][0]) < TOL and relF(outs[1][1], outs[0][1]) < TOL
+
+
+@pytest.mark.parametrize("F,N,K", [(257, 300, 33), (1000, 513, 128), (640, 1999, 65)])
+def test_tensor_path_ragged_shapes_and_empty_lines(F, N, K):
+    """Dimensions that are no multiple of any tile size, K at the edges of the padded ranges, plus a
+    row and a column with no observed entry at all (their statistics stay 0, E_H is the prior mean)."""
+    from nbmf_b200 import Engine, _lib
+    V, _, _ = oracle.generate(F, N, 4, 0.8, 0.8, 5)
+    V = V.copy(order="F")
+    V[np.random.default_rng(2).random(V.shape) < 0.1] = NA
+    V[3, :] = NA
+    V[:, 7] = NA
+    Z = oracle.random_labels(V, K, 3)
+    out = {}
+    for prec in (_lib.PREC_FP64, _lib.PREC_TENSOR):
+        e = Engine(precision=prec)
+        e.set_data(V); e.init_from_labels(Z, K)
+        out[prec] = e.vb_aspect(K, 1.0, 2.0, 0.7, iter=5, checklb=True) + (e.get_stats(K),)
+        e.close()
+    Wf, Hf, lf, _, sf = out[_lib.PREC_FP64]
+    Wt, Ht, lt, _, st = out[_lib.PREC_TENSOR]
+    assert relF(Wt, Wf) < TOL and relF(Ht, Hf) < TOL and np.max(np.abs(lt - lf) / np.abs(lf)) < TOL
+    assert np.all(st[0][3] == 0) and np.all(st[1][7] == 0) and np.all(st[2][7] == 0)
+    assert np.allclose(Ht[7], 1.0 / 3.0) and np.allclose(Wt[3], 1.0 / K)
+    if F * N * K < 3e7:   # and against the oracle itself where it finishes in seconds
+        ref = oracle.vb_aspect_batch(V, Z, K, 1.0, 2.0, 0.7, iter=5, checklb=True)
+        assert relF(Wf, ref["E_W"]) < 1e-9 and relF(Wt, ref["E_W"]) < TOL
