@@ -353,6 +353,22 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, volatil
     *abort_flag = code;
     return false;
 }
+// single probes (no loop): used to start a wait early and look at the answer later
+__device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok;
+}
+__device__ __forceinline__ uint32_t mbar_try2(uint32_t bar_a, uint32_t par_a, uint32_t bar_b, uint32_t par_b)
+{
+    uint32_t ok;
+    asm volatile("{\n .reg .pred p, q;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+                 " mbarrier.try_wait.parity.shared::cta.b64 q, [%3], %4;\n and.pred p, p, q;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(bar_a), "r"(par_a), "r"(bar_b), "r"(par_b) : "memory");
+    return ok;
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *tm, int c0, int c1, uint32_t bar)
 {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -454,6 +470,18 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int b_mn_major)
     return (1u << 4) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// cycle accounting per role (build with EXTRA=-DTP_PROFILE; tools/role_profile.py reads it)
+#ifdef TP_PROFILE
+__device__ unsigned long long g_tp_prof[64];
+#define PROF_DECL long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long pt0 = clock64(); (void)pt0
+#define PROF_ACC(i) do { long long pt1 = clock64(); pacc[i] += pt1 - pt0; pt0 = pt1; } while (0)
+#define PROF_OUT(role) do { if (blockIdx.x == 0) for (int i = 0; i < 8; i++) atomicAdd(&g_tp_prof[(role) * 8 + i], (unsigned long long)pacc[i]); } while (0)
+#else
+#define PROF_DECL
+#define PROF_ACC(i)
+#define PROF_OUT(role)
+#endif
+
 // ---------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------
@@ -475,40 +503,57 @@ struct TPArgs {
     int use_lo;                    // stage 2 adds the W_lo term (NBMF_PREC_TENSOR); 0 = hi only (NBMF_PREC_TENSOR_FAST)
 };
 
-// One step = 64 streamed rows.  Shared-memory stage: [hi: KB blocks][lo: KB blocks], each
-// block = 64 rows x 128 B (64 f16 of k), SWIZZLE_128B, written by TMA.  Seven stages (KP=128)
-// keep ~4 tiles in flight beyond the 3 that stage 1 / epilogue / stage 2 hold.
-// TMEM columns: G [0,KP) | 4 S slots of 64 columns [KP, KP+256) | U [KP+256, KP+256+KP/2).
-// Slot t&3 holds the stage-1 accumulators of step t; R (f16, 32 columns) is written back
-// over the slot.  Epilogue warpgroup g handles steps t = g (mod 2), i.e. slots g and g+2.
-template <int KP>
+// One step = 64 streamed rows.  Shared-memory stage: [hi: KB blocks]([lo: KB blocks] when the
+// W_lo term is on), each block = 64 rows x 128 B (64 f16 of k), SWIZZLE_128B, written by TMA.
+// A tile stays in its stage from the TMA issue until stage 2 has consumed it (~3000 cycles), so
+// the ring holds 7 stages (hi+lo, KP=128) or 14 (hi only).
+// TMEM columns: G [0,KP) | 3 S slots of 64 columns | 4 R slots of 32 columns | U (KP/2 columns).
+// Steps are numbered globally per CTA (gs, across work items); step gs uses S slot gs%3 and
+// R slot gs%4.  R does NOT overwrite S: the S slot is handed back as soon as the epilogue has
+// read it (SFREE), so stage 1 of step gs+3 runs while the epilogue of step gs is still
+// computing, and no epilogue group ever waits for a round trip through stage 2.
+//
+// Hand-off cost (tools/ubench/mbar_hop.cu, B200): an mbarrier try_wait takes ~170 cycles to
+// return even when the phase completed long ago, and arrive -> wake-up of a blocked waiter
+// ~180.  Both issuers therefore start the try_wait of step t+1 BEFORE they issue the MMAs of
+// step t and only fall back to a blocking wait when that early probe failed.
+template <int KP, bool USE_LO>
 struct TPCfg {
     static constexpr int KB = KP / 64;
     static constexpr int STEP_ROWS = 64;
     static constexpr int BLOCK_BYTES = STEP_ROWS * 128;
     static constexpr int PART_BYTES = KB * BLOCK_BYTES;     // hi (or lo) part of a stage
-    static constexpr int TILE_BYTES = 2 * PART_BYTES;
-    static constexpr int STAGES = (KP == 128) ? 7 : 12;
-    static constexpr int NSLOT = 4;
+    static constexpr int TILE_BYTES = (USE_LO ? 2 : 1) * PART_BYTES;
+    static constexpr int STAGES = (224 * 1024 / TILE_BYTES) > 16 ? 16 : (224 * 1024 / TILE_BYTES);
+    static constexpr int NS = 3;                            // S slots (fp32 stage-1 accumulators, 64 columns each)
+    static constexpr int NR = 4;                            // R slots (f16 reciprocals, 32 columns each)
     static constexpr int COL_G = 0;
-    static constexpr int COL_S = KP;                        // + 64 * slot
-    static constexpr int COL_U = KP + 256;
+    static constexpr int COL_S = KP;                        // + 64 * (step % NS)
+    static constexpr int COL_R = KP + 64 * NS;              // + 32 * (step % NR)
+    static constexpr int COL_U = COL_R + 32 * NR;           // KP/2 columns; KP = 128: 448 + 64 = 512
     static constexpr int SMEM_BYTES = STAGES * TILE_BYTES + 1024 /*align*/ + 512 /*barriers*/;
+    static_assert(2 * STAGES + NS + 3 * NR + 2 <= 64, "barrier area");
+    static_assert(SMEM_BYTES <= 227 * 1024, "shared memory");
 };
 
-template <int KP, bool ROWS, bool WANT_LOG, bool HAS_NA>
+template <int KP, bool ROWS, bool WANT_LOG, bool HAS_NA, bool USE_LO>
 __global__ void __launch_bounds__(TP_THREADS, 1)
 tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__ CUtensorMap tmLo, TPArgs a)
 {
-    using C = TPCfg<KP>;
+    using C = TPCfg<KP, USE_LO>;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = smem_base + C::STAGES * C::TILE_BYTES;
     auto BAR_FULL = [&](int s) { return bar_base + 8u * s; };
     auto BAR_EMPTY = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
-    const uint32_t BAR_SFULL = bar_base + 8u * (2 * C::STAGES);      // [4]
-    const uint32_t BAR_RREADY = BAR_SFULL + 8u * C::NSLOT;            // [4]
-    const uint32_t BAR_GFULL = BAR_RREADY + 8u * C::NSLOT;
+    // SFULL is indexed by step % 4 (= the epilogue group), not by S slot: a parity wait is only
+    // safe if the waiter cannot be two completions ahead, and a group knows that stage 1 of its
+    // previous step (gs-4), hence of every earlier step, has completed.
+    const uint32_t BAR_SFULL = bar_base + 8u * (2 * C::STAGES);      // [NR] stage 1 done          (commit)
+    const uint32_t BAR_SFREE = BAR_SFULL + 8u * C::NR;                // [NS] epilogue has read S    (128 arrivals)
+    const uint32_t BAR_RREADY = BAR_SFREE + 8u * C::NS;               // [NR] epilogue has written R (128 arrivals)
+    const uint32_t BAR_RFREE = BAR_RREADY + 8u * C::NR;               // [NR] stage 2 done           (commit)
+    const uint32_t BAR_GFULL = BAR_RFREE + 8u * C::NR;
     const uint32_t BAR_UREADY = BAR_GFULL + 8;
     __shared__ uint32_t tmem_base_sh;
     __shared__ int abort_sh;
@@ -519,7 +564,8 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
     if (threadIdx.x == 0) {
         abort_sh = 0;
         for (int s = 0; s < C::STAGES; s++) { mbar_init(BAR_FULL(s), 1); mbar_init(BAR_EMPTY(s), 1); }
-        for (int s = 0; s < C::NSLOT; s++) { mbar_init(BAR_SFULL + 8u * s, 1); mbar_init(BAR_RREADY + 8u * s, 128); }
+        for (int s = 0; s < C::NS; s++) mbar_init(BAR_SFREE + 8u * s, 128);
+        for (int s = 0; s < C::NR; s++) { mbar_init(BAR_SFULL + 8u * s, 1); mbar_init(BAR_RREADY + 8u * s, 128); mbar_init(BAR_RFREE + 8u * s, 1); }
         mbar_init(BAR_GFULL, 1);
         mbar_init(BAR_UREADY, 512);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -541,111 +587,165 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
         // ===================== TMA producer =====================
         if (elect_one()) {
             uint32_t stage = 0, phase = 0;
+            PROF_DECL;
             for (int64_t w = blockIdx.x; w < n_items; w += gridDim.x) {
                 const int chunk = (int)(w / a.owner_tiles);
                 const int64_t t0 = (int64_t)chunk * a.chunk_steps;
                 const int nst = (int)min((int64_t)a.chunk_steps, a.stream_steps - t0);
+                uint32_t pre = 0;
                 for (int t = 0; t < nst; t++) {
-                    if (!mbar_wait(BAR_EMPTY(stage), phase ^ 1, abort_flag, 1)) break;
+                    if (!pre && !mbar_wait(BAR_EMPTY(stage), phase ^ 1, abort_flag, 1)) break;
+                    PROF_ACC(0);
                     const uint32_t dst = smem_base + stage * C::TILE_BYTES;
+                    const uint32_t full = BAR_FULL(stage);
                     const int row0 = (int)((t0 + t) * C::STEP_ROWS);
-                    if (a.dbg_flags & 2) { mbar_arrive(BAR_FULL(stage)); }
-                    else if ((a.dbg_flags & 1) || !a.use_lo) {
-                        mbar_expect_tx(BAR_FULL(stage), C::PART_BYTES);
-                        for (int kb = 0; kb < C::KB; kb++) tma_load_2d(dst + kb * C::BLOCK_BYTES, &tmHi, kb * 64, row0, BAR_FULL(stage));
-                    } else {
-                    mbar_expect_tx(BAR_FULL(stage), C::TILE_BYTES);
-#pragma unroll
-                    for (int kb = 0; kb < C::KB; kb++) {
-                        tma_load_2d(dst + kb * C::BLOCK_BYTES, &tmHi, kb * 64, row0, BAR_FULL(stage));
-                        tma_load_2d(dst + C::PART_BYTES + kb * C::BLOCK_BYTES, &tmLo, kb * 64, row0, BAR_FULL(stage));
-                    }
-                    }
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                    pre = (t + 1 < nst) ? mbar_try(BAR_EMPTY(stage), phase ^ 1) : 0u;
+                    if (a.dbg_flags & 2) mbar_arrive(full);     // timing experiments only: no loads
+                    else {
+                        mbar_expect_tx(full, C::TILE_BYTES);
+#pragma unroll
+                        for (int kb = 0; kb < C::KB; kb++) {
+                            tma_load_2d(dst + kb * C::BLOCK_BYTES, &tmHi, kb * 64, row0, full);
+                            if (USE_LO) tma_load_2d(dst + C::PART_BYTES + kb * C::BLOCK_BYTES, &tmLo, kb * 64, row0, full);
+                        }
+                    }
+                    PROF_ACC(1);
                 }
                 if (*abort_flag) break;
             }
+            PROF_OUT(0);
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        // One elected thread; everything it touches is kept in registers (no indexed arrays)
-        // and descriptors are formed as {base_lo + constant, constant_hi}: the thread's own
-        // instruction stream must stay well below the tensor time of a step.
+        // ===================== MMA issuer, stage 1: S(slot gs%3) = U_hi . W_hi^T =====================
+        // Stage 1 and stage 2 are issued by two different threads (warps 1 and 3): a single
+        // thread's instruction stream (2 waits + 12 MMAs + 2 commits per step) took as long as
+        // the tensor pipe needs for the step.  Everything an issuer touches is kept in registers
+        // (no indexed arrays) and descriptors are formed as {base_lo + constant, constant_hi}.
+        // A wait on the parity *before* a barrier's first completion returns at once, which
+        // covers the first use of every slot.
         if (elect_one()) {
             constexpr uint32_t IDESC1 = make_idesc(128, C::STEP_ROWS, 0);
-            constexpr uint32_t IDESC2 = make_idesc(128, KP, 1);
-            // descriptor high words: SBO = 1024 B, version 1, SWIZZLE_128B (see make_desc)
-            constexpr uint32_t DHI = (1024u >> 4) | (1u << 14) | (2u << 29);
+            constexpr uint32_t DHI = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO = 1024 B, version 1, SWIZZLE_128B
             constexpr uint32_t DLO1 = (16u >> 4) << 16;                    // K-major: LBO field = 1
-            constexpr uint32_t DLO2 = ((uint32_t)C::BLOCK_BYTES >> 4) << 16; // MN-major: LBO = k-block stride
             uint32_t s_stage = 0, s_phase = 0;   // smem ring position of the next tile to run stage 1 on
-            uint32_t g_stage = 0;                // ... of the next tile to run stage 2 on
-            uint32_t rr_phase = 0;               // bit per slot
+            uint32_t slot = 0, use_par = 0;      // S slot of the next step and parity of its use count
+            uint32_t g4 = 0;                     // step % 4: the epilogue group that takes the step
             uint32_t u_phase = 0;
+            PROF_DECL;
             for (int64_t w = blockIdx.x; w < n_items; w += gridDim.x) {
                 const int chunk = (int)(w / a.owner_tiles);
                 const int64_t t0 = (int64_t)chunk * a.chunk_steps;
                 const int nst = (int)min((int64_t)a.chunk_steps, a.stream_steps - t0);
-                bool ok = mbar_wait(BAR_UREADY, u_phase, abort_flag, 2);
+                if (!mbar_wait(BAR_UREADY, u_phase, abort_flag, 2)) break;
                 u_phase ^= 1;
-                tc_fence_after();
-                auto stage1 = [&](int t) {   // wait for tile t, S(slot t&3) = U_hi . W_hi^T
-                    ok = ok && mbar_wait(BAR_FULL(s_stage), s_phase, abort_flag, 3);
+                bool ok = true;
+                uint32_t pre_a = 0, pre_b = 0;   // the early probes of this step's two barriers succeeded
+                PROF_ACC(0);
+                for (int t = 0; t < nst; t++) {
+                    if (!(pre_a && pre_b)) {
+                        if (!mbar_wait(BAR_SFREE + 8u * slot, use_par ^ 1u, abort_flag, 5)) { ok = false; break; }
+                        if (!mbar_wait(BAR_FULL(s_stage), s_phase, abort_flag, 3)) { ok = false; break; }
+                    }
                     tc_fence_after();
+                    PROF_ACC(1);
                     const uint32_t lo = (((smem_base + s_stage * C::TILE_BYTES) >> 4) & 0x3FFFu) | DLO1;
-                    const uint32_t d = tmem + C::COL_S + 64 * (t & 3);
+                    const uint32_t d = tmem + C::COL_S + 64 * slot;
+                    const uint32_t sfull = BAR_SFULL + 8u * g4;
+                    g4 = (g4 + 1u) & 3u;
+                    if (++s_stage == C::STAGES) { s_stage = 0; s_phase ^= 1; }
+                    if (++slot == C::NS) { slot = 0; use_par ^= 1u; }
+                    // (two separate probes whose predicates are only combined at the top of the next
+                    // iteration: anything that reads them here would stall the MMA issue below)
+                    pre_a = (t + 1 < nst) ? mbar_try(BAR_SFREE + 8u * slot, use_par ^ 1u) : 0u;
+                    pre_b = (t + 1 < nst) ? mbar_try(BAR_FULL(s_stage), s_phase) : 0u;
+                    PROF_ACC(2);
 #pragma unroll
                     for (int kk = 0; kk < KP / 16; kk++)
                         tc_mma_ts2(d, tmem + C::COL_U + kk * 8,
                                    lo + (((kk >> 2) * C::BLOCK_BYTES + (kk & 3) * 32) >> 4), DHI, IDESC1, kk ? 1u : 0u);
-                    tc_commit(BAR_SFULL + 8u * (t & 3));
-                    if (++s_stage == C::STAGES) { s_stage = 0; s_phase ^= 1; }
-                };
-                for (int t = 0; t < C::NSLOT && t < nst; t++) stage1(t);
-                for (int t = 0; t < nst && ok; t++) {
-                    const int slot = t & 3;
-                    ok = ok && mbar_wait(BAR_RREADY + 8u * slot, (rr_phase >> slot) & 1u, abort_flag, 4);
-                    rr_phase ^= 1u << slot;
+                    PROF_ACC(3);
+                    tc_commit(sfull);
+                    PROF_ACC(4);
+                }
+                if (!ok) break;
+            }
+            PROF_OUT(1);
+        }
+    } else if (warp == 3) {
+        // ===================== MMA issuer, stage 2: G += R(slot gs%4) . (W_hi [+ W_lo]) =====================
+        if (elect_one()) {
+            constexpr uint32_t IDESC2 = make_idesc(128, KP, 1);
+            constexpr uint32_t DHI = (1024u >> 4) | (1u << 14) | (2u << 29);
+            constexpr uint32_t DLO2 = ((uint32_t)C::BLOCK_BYTES >> 4) << 16; // MN-major: LBO = k-block stride
+            uint32_t g_stage = 0;                // smem ring position of the next tile to run stage 2 on
+            uint32_t gs = 0;                     // global step counter
+            uint32_t u_phase = 0;
+            PROF_DECL;
+            for (int64_t w = blockIdx.x; w < n_items; w += gridDim.x) {
+                const int chunk = (int)(w / a.owner_tiles);
+                const int64_t t0 = (int64_t)chunk * a.chunk_steps;
+                const int nst = (int)min((int64_t)a.chunk_steps, a.stream_steps - t0);
+                // G of the previous item has been drained (the epilogue arrives after the drain)
+                if (!mbar_wait(BAR_UREADY, u_phase, abort_flag, 6)) break;
+                u_phase ^= 1;
+                bool ok = true;
+                uint32_t pre = 0;
+                PROF_ACC(0);
+                for (int t = 0; t < nst; t++) {
+                    const uint32_t rs = gs & 3u;
+                    if (!pre && !mbar_wait(BAR_RREADY + 8u * rs, (gs >> 2) & 1u, abort_flag, 4)) { ok = false; break; }
                     tc_fence_after();
-                    // stage 2: G += R(slot) . (W_hi + W_lo), B operand MN-major (N = k contiguous)
+                    PROF_ACC(1);
+                    // B operand MN-major (N = k contiguous) from the same smem tile stage 1 read K-major
                     const uint32_t lo = (((smem_base + g_stage * C::TILE_BYTES) >> 4) & 0x3FFFu) | DLO2;
-                    const uint32_t rcol = tmem + C::COL_S + 64 * slot;
+                    const uint32_t rcol = tmem + C::COL_R + 32 * rs;
+                    const uint32_t empty = BAR_EMPTY(g_stage);
+                    if (++g_stage == C::STAGES) g_stage = 0;
+                    gs++;
+                    pre = (t + 1 < nst) ? mbar_try(BAR_RREADY + 8u * (gs & 3u), (gs >> 2) & 1u) : 0u;
 #pragma unroll
                     for (int j = 0; j < C::STEP_ROWS / 16; j++)
                         tc_mma_ts2(tmem + C::COL_G, rcol + j * 8, lo + ((j * (16 * 128)) >> 4), DHI, IDESC2,
                                    (t == 0 && j == 0) ? 0u : 1u);
-                    if (a.use_lo) {
+                    if (USE_LO) {
 #pragma unroll
                         for (int j = 0; j < C::STEP_ROWS / 16; j++)
                             tc_mma_ts2(tmem + C::COL_G, rcol + j * 8, lo + ((C::PART_BYTES + j * (16 * 128)) >> 4), DHI, IDESC2, 1u);
                     }
-                    tc_commit(BAR_EMPTY(g_stage));   // tile t fully consumed
-                    if (++g_stage == C::STAGES) g_stage = 0;
-                    if (t + C::NSLOT < nst) stage1(t + C::NSLOT);
+                    PROF_ACC(2);
+                    tc_commit(empty);                // tile consumed: the smem stage goes back to the producer
+                    tc_commit(BAR_RFREE + 8u * rs);  // ... and the R slot to the epilogue
+                    PROF_ACC(3);
                 }
                 tc_commit(BAR_GFULL);
                 if (!ok) break;
             }
+            PROF_OUT(2);
         }
     } else if (warp >= 4) {
         // ===================== epilogue =====================
-        // four warpgroups, one per TMEM slot: group g handles steps t = g (mod 4).  More resident
-        // warps than strictly needed for throughput: the step latency (TMEM load -> select ->
-        // rcp -> pack -> TMEM store -> mbarrier) is what the MMA issuer otherwise waits on.
-        const int grp = (warp - 4) >> 2;            // = slot
+        // four warpgroups; group g owns R slot g and handles the steps with gs = g (mod 4).  More
+        // resident warps than the arithmetic needs: one step's epilogue (TMEM load -> select ->
+        // rcp -> pack -> TMEM store -> mbarrier) lasts about two tensor steps.
+        const int grp = (warp - 4) >> 2;            // = R slot
         const int q = warp & 3;                     // TMEM lane quarter
         const int lrow = q * 32 + lane;             // owner lane within the tile
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-        const uint32_t t_s = tmem + lane_addr + C::COL_S + 64 * grp;
-        const uint32_t bar_sfull = BAR_SFULL + 8u * grp, bar_rready = BAR_RREADY + 8u * grp;
-        uint32_t sf_phase = 0, g_phase = 0;
+        const uint32_t t_r = tmem + lane_addr + C::COL_R + 32 * grp;
+        const uint32_t bar_sfull = BAR_SFULL + 8u * grp, bar_rready = BAR_RREADY + 8u * grp, bar_rfree = BAR_RFREE + 8u * grp;
+        uint32_t g_phase = 0;
+        uint32_t base = 0;                          // global step number of the item's first step
+        uint32_t r_par = 0;                         // parity of the use count of this group's R slot
+        PROF_DECL;
         const float c0 = exp2f((float)(eU + eW - 14));
         const float c1 = exp2f((float)(-(eU + eW)));   // S * c1 = D: lg2.approx's relative error must apply to log2 D, not to log2 S
-        const float finf = __int_as_float(0x7f800000);
+        const float fhuge = __int_as_float(0x5f800000);   // 2^64: stand-in for an unselected entry
+        const float ftiny = __int_as_float(0x21800000);   // 2^-60: keeps the shared reciprocal finite when S underflowed to 0
         double log_acc_total = 0.0;
         bool first_item = true, ok = true;
         int64_t prev_w = -1;
-        constexpr int GCOLS = (KP == 128) ? 32 : 32;          // G columns drained per group
+        constexpr int GCOLS = 32;                            // G columns drained per group
         constexpr int NDRAIN = KP / GCOLS;                   // groups that take part (4 or 2)
         auto drain_G = [&](int64_t pw) {
             if (grp < NDRAIN) {
@@ -693,7 +793,7 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
             mbar_arrive(BAR_UREADY);
             first_item = false;
             prev_w = w;
-            // ---- steps t = grp, grp+4, ...
+            // ---- steps with base + t = grp (mod 4)
             float log_acc = 0.f;
             const int64_t orow = ROWS ? l : (l >> 1);
             const uint32_t bsel = ROWS ? 0u : (uint32_t)(l & 1);
@@ -710,8 +810,10 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
                     bm[i] = HAS_NA ? (lane_ok ? __ldg(mrow + wi + i) : 0u) : 0xffffffffu;
                 }
             };
-            if (grp < nst) load_bits(grp);
-            for (int t = grp; t < nst && ok; t += 4) {
+            const int tfirst = (int)(((uint32_t)grp - base) & 3u);
+            if (tfirst < nst) load_bits(tfirst);
+            PROF_ACC(0);
+            for (int t = tfirst; t < nst && ok; t += 4) {
                 uint32_t sel[WPS], vv[WPS];
 #pragma unroll
                 for (int i = 0; i < WPS; i++) {
@@ -719,48 +821,82 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
                     sel[i] = ROWS ? bm[i] : ((bsel ? bv[i] : ~bv[i]) & bm[i]);
                 }
                 if (t + 4 < nst) load_bits(t + 4);
-                ok = ok && mbar_wait(bar_sfull, sf_phase, abort_flag, 8);
-                sf_phase ^= 1;
-                tc_fence_after();
-#pragma unroll
-                for (int cc = 0; cc < 2; cc++) {
-                    uint32_t s[32], rp[16];
-                    tc_ld32(t_s + cc * 32, s);
-                    tc_wait_ld();
-                    if (a.dbg != nullptr && w == 0 && t < 4) {
-                        for (int i = 0; i < 32; i++) a.dbg[(lrow * 256) + t * 64 + cc * 32 + i] = __uint_as_float(s[i]);
-                    }
+                const uint32_t gs = base + (uint32_t)t;
+                const uint32_t s_use = gs / 3u, sslot = gs - 3u * s_use;
+                const uint32_t t_s = tmem + lane_addr + C::COL_S + 64 * sslot;
+                // one half (32 S columns) of the step: select, shared reciprocal, pack to f16
+                auto half_step = [&](const int cc, const uint32_t (&s)[32], uint32_t (&rp)[16]) {
                     if (ROWS) {
                         // 32 columns = 16 entries (n) x 2 branches, column 2j+b
                         const uint32_t m16 = sel[0] >> (cc * 16);
                         const uint32_t v16 = vv[0] >> (cc * 16);
 #pragma unroll
-                        for (int j = 0; j < 16; j++) {
-                            const bool vb = (v16 >> j) & 1u;
-                            float sv = __uint_as_float(vb ? s[2 * j + 1] : s[2 * j]);
+                        for (int i = 0; i < 8; i++) {
+                            // two entries share one reciprocal: 1/s0 = s1/(s0 s1), 1/s1 = s0/(s0 s1);
+                            // a masked entry takes part as 2^64, which makes its own R vanish below
+                            // f16 resolution and leaves its partner's R exact
+                            const int j0 = 2 * i, j1 = 2 * i + 1;
+                            const bool vb0 = (v16 >> j0) & 1u, vb1 = (v16 >> j1) & 1u;
+                            float s0 = __uint_as_float(vb0 ? s[2 * j0 + 1] : s[2 * j0]);
+                            float s1 = __uint_as_float(vb1 ? s[2 * j1 + 1] : s[2 * j1]);
                             if (HAS_NA) {
-                                const bool mb = (m16 >> j) & 1u;
-                                if (WANT_LOG) log_acc += mb ? fast_lg2(sv * c1) : 0.f;
-                                sv = mb ? sv : finf;                 // masked entry: R = 0
-                            } else if (WANT_LOG) log_acc += fast_lg2(sv * c1);
-                            const float r = c0 * fast_rcp(sv);
-                            rp[j] = pack_h2_sat(vb ? 0.f : r, vb ? r : 0.f);
+                                const bool mb0 = (m16 >> j0) & 1u, mb1 = (m16 >> j1) & 1u;
+                                if (WANT_LOG) log_acc += fast_lg2((mb0 ? s0 * c1 : 1.f) * (mb1 ? s1 * c1 : 1.f));
+                                s0 = mb0 ? s0 : fhuge;
+                                s1 = mb1 ? s1 : fhuge;
+                            } else if (WANT_LOG) log_acc += fast_lg2((s0 * c1) * (s1 * c1));
+                            const float tr = c0 * fast_rcp(fmaf(s0, s1, ftiny));
+                            const float r0 = tr * s1, r1 = tr * s0;
+                            rp[j0] = pack_h2_sat(vb0 ? 0.f : r0, vb0 ? r0 : 0.f);
+                            rp[j1] = pack_h2_sat(vb1 ? 0.f : r1, vb1 ? r1 : 0.f);
                         }
                     } else {
                         const uint32_t m32 = sel[cc];
 #pragma unroll
                         for (int j = 0; j < 16; j++) {
-                            const float a0 = ((m32 >> (2 * j)) & 1u) ? __uint_as_float(s[2 * j]) : finf;
-                            const float a1 = ((m32 >> (2 * j + 1)) & 1u) ? __uint_as_float(s[2 * j + 1]) : finf;
-                            rp[j] = pack_h2_sat(c0 * fast_rcp(a0), c0 * fast_rcp(a1));
+                            const float a0 = ((m32 >> (2 * j)) & 1u) ? __uint_as_float(s[2 * j]) : fhuge;
+                            const float a1 = ((m32 >> (2 * j + 1)) & 1u) ? __uint_as_float(s[2 * j + 1]) : fhuge;
+                            const float tr = c0 * fast_rcp(fmaf(a0, a1, ftiny));
+                            rp[j] = pack_h2_sat(tr * a1, tr * a0);
                         }
                     }
-                    tc_st16(t_s + cc * 16, rp);
-                }
+                };
+                PROF_ACC(1);
+                ok = ok && mbar_wait(bar_sfull, r_par, abort_flag, 8);
+                tc_fence_after();
+                PROF_ACC(2);
+                uint32_t s[32], rp0[16], rp1[16];
+                tc_ld32(t_s, s);
+                // stage 2 of step gs-4 must be done with the R slot: probe now, look at the answer later
+                const uint32_t rfree = mbar_try(bar_rfree, r_par ^ 1u);
+                tc_wait_ld();
+                if (a.dbg != nullptr && w == 0 && t < 4)
+                    for (int i = 0; i < 32; i++) a.dbg[(lrow * 256) + t * 64 + i] = __uint_as_float(s[i]);
+                PROF_ACC(3);
+                half_step(0, s, rp0);
+                PROF_ACC(4);
+                tc_ld32(t_s + 32, s);
+                tc_wait_ld();
+                // S has been read: stage 1 of step gs+3 may overwrite the slot
+                tc_fence_before();
+                mbar_arrive(BAR_SFREE + 8u * sslot);
+                if (a.dbg != nullptr && w == 0 && t < 4)
+                    for (int i = 0; i < 32; i++) a.dbg[(lrow * 256) + t * 64 + 32 + i] = __uint_as_float(s[i]);
+                PROF_ACC(3);
+                if (!rfree) ok = ok && mbar_wait(bar_rfree, r_par ^ 1u, abort_flag, 10);
+                tc_fence_after();
+                PROF_ACC(5);
+                tc_st16(t_r, rp0);
+                half_step(1, s, rp1);
+                PROF_ACC(4);
+                tc_st16(t_r + 16, rp1);
                 tc_wait_st();
                 tc_fence_before();
                 mbar_arrive(bar_rready);
+                r_par ^= 1u;
+                PROF_ACC(6);
             }
+            base += (uint32_t)nst;
             if (WANT_LOG) log_acc_total += (double)log_acc;
         }
         // ---- drain G of the last item
@@ -773,6 +909,9 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
             double v = warp_sum(log_acc_total);
             if (lane == 0) atomicAdd(&a.dacc[0], v);
         }
+#ifdef TP_PROFILE
+        if (q == 0 && lane == 0) PROF_OUT(3 + grp);
+#endif
     }
     tc_fence_before();
     __syncthreads();
@@ -801,19 +940,21 @@ __global__ void tp_logfix_kernel(const double *dacc, const int *dexp, double nse
         *sumlogD += 0.6931471805599453 * dacc[0];
 }
 
-template <int KP, bool ROWS, bool WANT_LOG, bool HAS_NA>
-static cudaError_t launch_tp2(const CUtensorMap &tm, const CUtensorMap &tmlo, const TPArgs &a, int grid, cudaStream_t st)
+template <int KP, bool ROWS, bool WANT_LOG, bool HAS_NA, bool USE_LO>
+static cudaError_t launch_tp3(const CUtensorMap &tm, const CUtensorMap &tmlo, const TPArgs &a, int grid, cudaStream_t st)
 {
-    cudaError_t e = cudaFuncSetAttribute(tp_pass_kernel<KP, ROWS, WANT_LOG, HAS_NA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         TPCfg<KP>::SMEM_BYTES);
+    auto kern = tp_pass_kernel<KP, ROWS, WANT_LOG, HAS_NA, USE_LO>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TPCfg<KP, USE_LO>::SMEM_BYTES);
     if (e != cudaSuccess) return e;
-    tp_pass_kernel<KP, ROWS, WANT_LOG, HAS_NA><<<grid, TP_THREADS, TPCfg<KP>::SMEM_BYTES, st>>>(tm, tmlo, a);
+    kern<<<grid, TP_THREADS, TPCfg<KP, USE_LO>::SMEM_BYTES, st>>>(tm, tmlo, a);
     return cudaGetLastError();
 }
 template <int KP, bool ROWS, bool WANT_LOG>
 static cudaError_t launch_tp(const CUtensorMap &tm, const CUtensorMap &tmlo, const TPArgs &a, int grid, cudaStream_t st, bool has_na)
 {
-    return has_na ? launch_tp2<KP, ROWS, WANT_LOG, true>(tm, tmlo, a, grid, st) : launch_tp2<KP, ROWS, WANT_LOG, false>(tm, tmlo, a, grid, st);
+    if (a.use_lo)
+        return has_na ? launch_tp3<KP, ROWS, WANT_LOG, true, true>(tm, tmlo, a, grid, st) : launch_tp3<KP, ROWS, WANT_LOG, false, true>(tm, tmlo, a, grid, st);
+    return has_na ? launch_tp3<KP, ROWS, WANT_LOG, true, false>(tm, tmlo, a, grid, st) : launch_tp3<KP, ROWS, WANT_LOG, false, false>(tm, tmlo, a, grid, st);
 }
 
 static float *g_tp_dbg = nullptr; // set by nbmf_debug_tp_dump only
@@ -914,6 +1055,16 @@ int tp_check_error(nbmf_handle *h)
 // Debug aid (not part of the public header): runs params + one pass and returns the raw
 // stage-1 accumulators S (128 owner lanes x 256 streamed rows, fp32) of the first work
 // item's first step, plus the operand exponents.
+#ifdef TP_PROFILE
+extern "C" int nbmf_debug_tp_prof(unsigned long long *out64, int reset)
+{
+    cudaDeviceSynchronize();
+    if (out64) cudaMemcpyFromSymbol(out64, g_tp_prof, sizeof(unsigned long long) * 64);
+    if (reset) { unsigned long long z[64] = {0}; cudaMemcpyToSymbol(g_tp_prof, z, sizeof(z)); }
+    return 0;
+}
+#endif
+
 extern "C" int nbmf_debug_tp_dump(nbmf_handle *h, int owner_rows, float *S_out, int *exps_out)
 {
     TPState *s = (TPState *)h->tp;
