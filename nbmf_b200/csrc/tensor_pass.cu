@@ -865,29 +865,29 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
                 ok = ok && mbar_wait(bar_sfull, r_par, abort_flag, 8);
                 tc_fence_after();
                 PROF_ACC(2);
-                uint32_t s[32], rp0[16], rp1[16];
-                tc_ld32(t_s, s);
+                // both halves of S are loaded before any arithmetic so that the slot goes back to the
+                // stage-1 issuer one TMEM-load latency after stage 1 completed
+                uint32_t s0[32], s1[32], rp0[16], rp1[16];
+                tc_ld32(t_s, s0);
+                tc_ld32(t_s + 32, s1);
                 // stage 2 of step gs-4 must be done with the R slot: probe now, look at the answer later
                 const uint32_t rfree = mbar_try(bar_rfree, r_par ^ 1u);
                 tc_wait_ld();
-                if (a.dbg != nullptr && w == 0 && t < 4)
-                    for (int i = 0; i < 32; i++) a.dbg[(lrow * 256) + t * 64 + i] = __uint_as_float(s[i]);
-                PROF_ACC(3);
-                half_step(0, s, rp0);
-                PROF_ACC(4);
-                tc_ld32(t_s + 32, s);
-                tc_wait_ld();
-                // S has been read: stage 1 of step gs+3 may overwrite the slot
                 tc_fence_before();
                 mbar_arrive(BAR_SFREE + 8u * sslot);
                 if (a.dbg != nullptr && w == 0 && t < 4)
-                    for (int i = 0; i < 32; i++) a.dbg[(lrow * 256) + t * 64 + 32 + i] = __uint_as_float(s[i]);
+                    for (int i = 0; i < 32; i++) {
+                        a.dbg[(lrow * 256) + t * 64 + i] = __uint_as_float(s0[i]);
+                        a.dbg[(lrow * 256) + t * 64 + 32 + i] = __uint_as_float(s1[i]);
+                    }
                 PROF_ACC(3);
+                half_step(0, s0, rp0);
+                PROF_ACC(4);
                 if (!rfree) ok = ok && mbar_wait(bar_rfree, r_par ^ 1u, abort_flag, 10);
                 tc_fence_after();
                 PROF_ACC(5);
                 tc_st16(t_r, rp0);
-                half_step(1, s, rp1);
+                half_step(1, s1, rp1);
                 PROF_ACC(4);
                 tc_st16(t_r + 16, rp1);
                 tc_wait_st();
