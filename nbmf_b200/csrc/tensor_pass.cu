@@ -337,22 +337,6 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
     asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"(bar), "r"(bytes)
                  : "memory");
 }
-// bounded wait: on timeout raise the CTA-wide abort flag so that the kernel drains
-// instead of hanging the GPU; the host reports the error.
-__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, volatile int *abort_flag, int code)
-{
-    uint32_t ok = 0;
-    for (uint32_t spin = 0; spin < TP_SPIN_LIMIT; spin++) {
-        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(ok)
-                     : "r"(bar), "r"(parity)
-                     : "memory");
-        if (ok) return true;
-        if ((spin & 1023u) == 1023u && *abort_flag) return false;
-    }
-    *abort_flag = code;
-    return false;
-}
 // single probes (no loop): used to start a wait early and look at the answer later
 __device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity)
 {
@@ -368,6 +352,20 @@ __device__ __forceinline__ uint32_t mbar_try2(uint32_t bar_a, uint32_t par_a, ui
                  " mbarrier.try_wait.parity.shared::cta.b64 q, [%3], %4;\n and.pred p, p, q;\n selp.u32 %0, 1, 0, p;\n}"
                  : "=r"(ok) : "r"(bar_a), "r"(par_a), "r"(bar_b), "r"(par_b) : "memory");
     return ok;
+}
+// bounded wait: on timeout raise the CTA-wide abort flag so that the kernel drains
+// instead of hanging the GPU; the host reports the error.  The first probe is the hot path
+// (one instruction, no loop state); the retry loop is kept rolled.
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, volatile int *abort_flag, int code)
+{
+    if (mbar_try(bar, parity)) return true;
+#pragma unroll 1
+    for (uint32_t spin = 1; spin < TP_SPIN_LIMIT; spin++) {
+        if (mbar_try(bar, parity)) return true;
+        if ((spin & 1023u) == 0u && *abort_flag) return false;
+    }
+    *abort_flag = code;
+    return false;
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *tm, int c0, int c1, uint32_t bar)
 {
@@ -875,11 +873,13 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
                 tc_wait_ld();
                 tc_fence_before();
                 mbar_arrive(BAR_SFREE + 8u * sslot);
+#ifdef TP_DEBUG_DUMP
                 if (a.dbg != nullptr && w == 0 && t < 4)
                     for (int i = 0; i < 32; i++) {
                         a.dbg[(lrow * 256) + t * 64 + i] = __uint_as_float(s0[i]);
                         a.dbg[(lrow * 256) + t * 64 + 32 + i] = __uint_as_float(s1[i]);
                     }
+#endif
                 PROF_ACC(3);
                 half_step(0, s0, rp0);
                 PROF_ACC(4);
@@ -1065,8 +1065,14 @@ extern "C" int nbmf_debug_tp_prof(unsigned long long *out64, int reset)
 }
 #endif
 
+// raw stage-1 accumulators of the first tile (tools/tp_probe.py); only a library built with
+// EXTRA=-DTP_DEBUG_DUMP carries the dump code in the kernel
 extern "C" int nbmf_debug_tp_dump(nbmf_handle *h, int owner_rows, float *S_out, int *exps_out)
 {
+#ifndef TP_DEBUG_DUMP
+    h->err = "library built without -DTP_DEBUG_DUMP";
+    return NBMF_ERR_STATE;
+#endif
     TPState *s = (TPState *)h->tp;
     if (!s) { h->err = "no tensor state (call nbmf_vb_begin with a tensor precision first)"; return NBMF_ERR_STATE; }
     float *d = nullptr;
