@@ -39,26 +39,57 @@ __global__ void pack_cols_kernel(const int32_t *__restrict__ V, int64_t F, int64
     }
 }
 
-// 32x32 bit-tile transpose: src [R][Ws] packed along c  ->  dst [C][Wd] packed
-// along r.  One warp per (32-row group, source word).
-__global__ void transpose_bits_kernel(const uint32_t *__restrict__ src, int64_t R, int64_t Ws,
-                                      int64_t C, uint32_t *__restrict__ dst, int64_t Wd)
+// 32x32 bit transpose across a warp: lane l holds row l (bit c = element (l, c)) and ends up
+// with column l (bit r = element (r, l)).  Five butterfly steps, each swapping the off-diagonal
+// j x j blocks between lanes l and l ^ j.
+__device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, int lane)
 {
-    int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    int lane = threadIdx.x & 31;
-    int64_t rg = (R + 31) / 32, cw = (C + 31) / 32;
-    if (warp >= rg * cw) return;
-    int64_t g = warp / cw, w = warp % cw;
-    int64_t r = g * 32 + lane;
-    uint32_t word = (r < R) ? src[r * Ws + w] : 0u;
-    uint32_t keep = 0;
 #pragma unroll
-    for (int i = 0; i < 32; i++) {
-        uint32_t b = __ballot_sync(0xffffffffu, (word >> i) & 1u);
-        if (lane == i) keep = b;
+    for (int j = 16; j >= 1; j >>= 1) {
+        // m: j ones, j zeros, ... from the least significant bit
+        const uint32_t m = (j == 16) ? 0x0000ffffu : (j == 8) ? 0x00ff00ffu : (j == 4) ? 0x0f0f0f0fu
+                         : (j == 2) ? 0x33333333u : 0x55555555u;
+        const uint32_t y = __shfl_xor_sync(0xffffffffu, x, j);
+        const bool upper = (lane & j) == 0;
+        const uint32_t t = upper ? (y << j) : (y >> j);
+        const uint32_t keep = upper ? m : ~m;
+        x = (x & keep) | (t & ~keep);
     }
-    int64_t c = w * 32 + lane;
-    if (c < C) dst[c * Wd + g] = keep;
+    return x;
+}
+
+// Bit-plane transpose: src [R][Ws] packed along c  ->  dst [C][Wd] packed along r.
+// One block = 8 row groups (256 rows) x 16 source words: the tile is read as 64-byte row
+// segments, every warp transposes the 8 32x32 bit tiles of one source word, and the result
+// leaves as 32-byte runs (8 consecutive destination words per destination row).
+#define TB_GROUPS 8
+#define TB_WORDS 16
+__global__ void __launch_bounds__(TB_WORDS * 32)
+transpose_bits_kernel(const uint32_t *__restrict__ src, int64_t R, int64_t Ws,
+                      int64_t C, uint32_t *__restrict__ dst, int64_t Wd)
+{
+    __shared__ uint32_t tin[TB_GROUPS * 32][TB_WORDS + 1];
+    __shared__ uint32_t tout[TB_WORDS * 32][TB_GROUPS + 1];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t cw = (C + 31) / 32;
+    const int64_t w0 = (int64_t)blockIdx.x * TB_WORDS, g0 = (int64_t)blockIdx.y * TB_GROUPS;
+    for (int i = threadIdx.x; i < TB_GROUPS * 32 * TB_WORDS; i += TB_WORDS * 32) {
+        const int rr = i / TB_WORDS, ww = i % TB_WORDS;
+        const int64_t r = g0 * 32 + rr, w = w0 + ww;
+        tin[rr][ww] = (r < R && w < cw) ? src[r * Ws + w] : 0u;
+    }
+    __syncthreads();
+    // warp = source word w0 + warp
+#pragma unroll
+    for (int g = 0; g < TB_GROUPS; g++)
+        tout[warp * 32 + lane][g] = warp_transpose32(tin[g * 32 + lane][warp], lane);
+    __syncthreads();
+    const int64_t gw = (R + 31) / 32;
+    for (int i = threadIdx.x; i < TB_WORDS * 32 * TB_GROUPS; i += TB_WORDS * 32) {
+        const int row = i / TB_GROUPS, g = i % TB_GROUPS;
+        const int64_t c = w0 * 32 + row;
+        if (c < C && g0 + g < gw) dst[c * Wd + g0 + g] = tout[row][g];
+    }
 }
 
 __global__ void popcount_kernel(const uint32_t *__restrict__ m, int64_t count, unsigned long long *out)

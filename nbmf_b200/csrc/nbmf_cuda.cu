@@ -192,12 +192,13 @@ static int alloc_planes(nbmf_handle *h, int64_t F, int64_t N)
 static int build_row_planes(nbmf_handle *h)
 {
     int64_t rg = (h->N + 31) / 32, cw = (h->F + 31) / 32;
-    int64_t warps = rg * cw;
-    transpose_bits_kernel<<<nblk(warps * 32, 256), 256, 0, h->stream>>>(h->vc, h->N, h->Fw, h->F,
-                                                                        h->vr, h->Nw);
+    dim3 grid((unsigned)((cw + TB_WORDS - 1) / TB_WORDS), (unsigned)((rg + TB_GROUPS - 1) / TB_GROUPS));
+    transpose_bits_kernel<<<grid, TB_WORDS * 32, 0, h->stream>>>(h->vc, h->N, h->Fw, h->F, h->vr, h->Nw);
     LAUNCH_CHECK();
-    transpose_bits_kernel<<<nblk(warps * 32, 256), 256, 0, h->stream>>>(h->mc, h->N, h->Fw, h->F,
-                                                                        h->mr, h->Nw);
+    if (h->has_na)
+        transpose_bits_kernel<<<grid, TB_WORDS * 32, 0, h->stream>>>(h->mc, h->N, h->Fw, h->F, h->mr, h->Nw);
+    else   // every entry observed: the transposed mask is known without reading anything
+        fill_mask_kernel<<<nblk(h->F * h->Nw, 256), 256, 0, h->stream>>>(h->mr, h->F, h->Nw, h->N);
     LAUNCH_CHECK();
     return NBMF_OK;
 }
