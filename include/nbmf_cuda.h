@@ -64,7 +64,7 @@ typedef struct nbmf_opts {
     int device;          /* CUDA ordinal                                                    */
     int precision;       /* nbmf_precision                                                  */
     int flush_interval;  /* tensor path: steps between TMEM accumulator flushes; 0 = default */
-    int reserved0;
+    int pipe_block_cols; /* nbmf_vb_aspect_bits: columns per upload block; 0 = default (32768)  */
     int64_t n_global;    /* column sharding: total number of columns (0 = not sharded)      */
     int64_t n_offset;    /* first global column this handle owns                            */
 } nbmf_opts;
@@ -141,6 +141,16 @@ int nbmf_get_stats(nbmf_handle *h, int Kc, double *n_total, double *f_ones, doub
  * Requires data + initial statistics with Kc == K.                            */
 int nbmf_vb_aspect(nbmf_handle *h, int K, double alpha, double beta, double gamma, int iter,
                    int checklb, double *E_W, double *E_H, double *lowerbounds, double *E_Z);
+/* The same call with V and the initial statistics taken from HOST memory, i.e. the whole of
+ * VB_Aspect_Rcpp(V, Z, ...) (collapsed_gibbs_z_VB.cpp:373-526) behind one entry point: vbits is
+ * the column-packed bit plane of nbmf_set_data_bits (no NA), n_total / f_ones / f_zeros the
+ * vbcounts of nbmf_set_stats.  The upload is cut into column blocks and the first iteration
+ * consumes them as they arrive, so the host->device transfer overlaps the contraction; pinned
+ * host memory is needed for that overlap (pageable memory still works, serially).        */
+int nbmf_vb_aspect_bits(nbmf_handle *h, const uint32_t *vbits, int64_t F, int64_t N, int K,
+                        double alpha, double beta, double gamma, int iter, int checklb,
+                        const double *n_total, const double *f_ones, const double *f_zeros,
+                        double *E_W, double *E_H, double *lowerbounds);
 /* the same, one iteration at a time (what bench.py times):
  *   begin -> step x iter -> end                                               */
 int nbmf_vb_begin(nbmf_handle *h, int K, double alpha, double beta, double gamma, int mean_params);

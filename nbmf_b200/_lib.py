@@ -19,7 +19,7 @@ DIRBER_EXACT_WAVEFRONT, DIRBER_CONTRACTION = 0, 1
 
 class NbmfOpts(C.Structure):
     _fields_ = [("device", C.c_int), ("precision", C.c_int), ("flush_interval", C.c_int),
-                ("reserved0", C.c_int), ("n_global", C.c_int64), ("n_offset", C.c_int64)]
+                ("pipe_block_cols", C.c_int), ("n_global", C.c_int64), ("n_offset", C.c_int64)]
 
 
 class NbmfTiming(C.Structure):
@@ -57,6 +57,8 @@ SYMBOLS = {
     "nbmf_set_stats": (C.c_int, [_H, C.c_int, _dp, _dp, _dp]),
     "nbmf_get_stats": (C.c_int, [_H, C.c_int, _dp, _dp, _dp]),
     "nbmf_vb_aspect": (C.c_int, [_H, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, _dp, _dp, _dp, _dp]),
+    "nbmf_vb_aspect_bits": (C.c_int, [_H, _up, C.c_int64, C.c_int64, C.c_int, C.c_double, C.c_double, C.c_double,
+                                      C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp]),
     "nbmf_vb_begin": (C.c_int, [_H, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int]),
     "nbmf_vb_step": (C.c_int, [_H, C.c_int]),
     "nbmf_vb_end": (C.c_int, [_H, _dp, _dp, _dp, C.c_int, _dp]),

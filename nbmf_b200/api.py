@@ -51,10 +51,10 @@ class Engine:
     """One libnbmf_cuda handle = one GPU's share of V (all of it unless sharded)."""
 
     def __init__(self, device: int = 0, precision: int = _lib.PREC_AUTO, flush_interval: int = 0,
-                 n_global: int = 0, n_offset: int = 0):
+                 n_global: int = 0, n_offset: int = 0, pipe_block_cols: int = 0):
         self.lib = _lib.load()
         self.h = C.c_void_p()
-        opts = NbmfOpts(device, precision, flush_interval, 0, n_global, n_offset)
+        opts = NbmfOpts(device, precision, flush_interval, pipe_block_cols, n_global, n_offset)
         rc = self.lib.nbmf_create(C.byref(self.h), C.byref(opts))
         if rc != 0:
             raise NbmfError(rc, "nbmf_create failed (no CUDA device? there is no CPU fallback)")
@@ -179,6 +179,26 @@ class Engine:
         self._ck(self.lib.nbmf_vb_aspect(self.h, K, alpha, beta, gamma, iter, int(checklb), _ptr(E_W, _dp),
                                          _ptr(E_H, _dp), _ptr(lbs, _dp), _ptr(E_Z, _dp)))
         return E_W, E_H, lbs[:iter], E_Z
+
+    def vb_aspect_bits(self, vbits, F, N, K, stats, alpha=1.0, beta=1.0, gamma=1.0, iter=100, checklb=False, out=None):
+        """VB_Aspect_Rcpp from host memory in one call (nbmf_vb_aspect_bits): `vbits` the column-packed
+        bit plane [N][ceil(F/32)] (no NA), `stats` = (n_total F x K, f_ones N x K, f_zeros N x K)
+        column-major fp64.  The upload overlaps the first iteration when `vbits` is pinned."""
+        vbits = np.ascontiguousarray(vbits, dtype=np.uint32)
+        assert vbits.shape == (N, (F + 31) // 32)
+        nt, fo, fz = (np.asfortranarray(x, dtype=np.float64) for x in stats)
+        assert nt.shape == (F, K) and fo.shape == (N, K) and fz.shape == (N, K)
+        self.F, self.N = F, N
+        if out is not None:
+            E_W, E_H = out
+            assert E_W.shape == (F, K) and E_H.shape == (N, K) and E_W.flags.f_contiguous and E_H.flags.f_contiguous
+        else:
+            E_W = np.zeros((F, K), order="F"); E_H = np.zeros((N, K), order="F")
+        lbs = np.zeros(max(iter, 1))
+        self._ck(self.lib.nbmf_vb_aspect_bits(self.h, _ptr(vbits, _up), F, N, K, alpha, beta, gamma, iter, int(checklb),
+                                              _ptr(nt, _dp), _ptr(fo, _dp), _ptr(fz, _dp), _ptr(E_W, _dp), _ptr(E_H, _dp),
+                                              _ptr(lbs, _dp)))
+        return E_W, E_H, lbs[:iter]
 
     def vb_begin(self, K, alpha=1.0, beta=1.0, gamma=1.0, mean_params=False):
         self._vbK = K

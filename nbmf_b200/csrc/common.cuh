@@ -57,6 +57,11 @@ struct nbmf_handle {
     nbmf_allreduce_fn hook = nullptr; void *hook_ctx = nullptr;
     nbmf_timing timing{};
     cudaEvent_t ev[8] = {};
+    // pipelined upload (nbmf_vb_aspect_bits): copy stream, one event per column block
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t pipe_ev[33] = {};
+    int64_t pipe_n0[34] = {};
+    int pipe_blocks = 0;                   // > 0 while the first step of a pipelined call is pending
 };
 
 enum { SC_SUMLOGD = 0, SC_PRIOR_ROWS = 1, SC_PRIOR_COLS = 2, SC_NEG = 3, SC_TMP = 4, SC_COUNT = 8 };

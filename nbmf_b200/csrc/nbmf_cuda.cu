@@ -103,6 +103,8 @@ extern "C" void nbmf_destroy(nbmf_handle *h)
     free_data(h); free_model(h);
     cudaFree(h->scal); cudaFree(h->lbs); cudaFree(h->stage);
     for (int i = 0; i < 8; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    for (int i = 0; i < 33; i++) if (h->pipe_ev[i]) cudaEventDestroy(h->pipe_ev[i]);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -164,11 +166,10 @@ static int alloc_planes(nbmf_handle *h, int64_t F, int64_t N)
 {
     CK(cudaSetDevice(h->device));
     if (h->vc && h->F == F && h->N == N) { // same shape (e.g. one C-ABI call per VB iteration): keep every buffer
-        size_t cb0 = (size_t)N * h->Fw * 4, rb0 = (size_t)F * h->Nw * 4;
+        // every loader rewrites all data words with plain stores and never touches the padding
+        // words, which are still zero from the allocation: nothing to clear
         cudaFree(h->Z); h->Z = nullptr;
         h->nobs = 0;
-        CK(cudaMemsetAsync(h->vc, 0, cb0, h->stream)); CK(cudaMemsetAsync(h->mc, 0, cb0, h->stream));
-        CK(cudaMemsetAsync(h->vr, 0, rb0, h->stream)); CK(cudaMemsetAsync(h->mr, 0, rb0, h->stream));
         tp_invalidate_data(h);
         return NBMF_OK;
     }
@@ -199,6 +200,18 @@ static int build_row_planes(nbmf_handle *h)
         transpose_bits_kernel<<<grid, TB_WORDS * 32, 0, h->stream>>>(h->mc, h->N, h->Fw, h->F, h->mr, h->Nw);
     else   // every entry observed: the transposed mask is known without reading anything
         fill_mask_kernel<<<nblk(h->F * h->Nw, 256), 256, 0, h->stream>>>(h->mr, h->F, h->Nw, h->N);
+    LAUNCH_CHECK();
+    return NBMF_OK;
+}
+
+// the part of the row-packed plane that columns [c0, c1) contribute (c0 a multiple of 32); the
+// data has no NA on this path, so the mask planes are filled up front
+static int build_row_planes_block(nbmf_handle *h, int64_t c0, int64_t c1)
+{
+    int64_t rg = (c1 - c0 + 31) / 32, cw = (h->F + 31) / 32;
+    dim3 grid((unsigned)((cw + TB_WORDS - 1) / TB_WORDS), (unsigned)((rg + TB_GROUPS - 1) / TB_GROUPS));
+    transpose_bits_kernel<<<grid, TB_WORDS * 32, 0, h->stream>>>(h->vc + c0 * h->Fw, c1 - c0, h->Fw, h->F,
+                                                               h->vr + c0 / 32, h->Nw);
     LAUNCH_CHECK();
     return NBMF_OK;
 }
@@ -591,6 +604,19 @@ extern "C" int nbmf_vb_step(nbmf_handle *h, int checklb)
     CK(cudaEventRecord(h->ev[1], h->stream));
     if ((rc = run_params(h, h->vb_K, h->vb_alpha, h->vb_beta, h->vb_gamma, h->vb_mean_params, checklb))) return rc;
     CK(cudaEventRecord(h->ev[2], h->stream));
+    if (h->pipe_blocks > 0) {
+        // first step of nbmf_vb_aspect_bits: both passes, column block by column block, as the
+        // upload of V arrives; reductions, exchange and corrections follow once
+        const int nb = h->pipe_blocks;
+        h->pipe_blocks = 0;
+        if ((rc = tp_passes_pipelined(h, nb, h->pipe_n0, h->pipe_ev, build_row_planes_block,
+                                      checklb ? h->scal + SC_SUMLOGD : nullptr))) return rc;
+        if (checklb && (rc = tp_log_correction(h, 1, h->scal + SC_SUMLOGD))) return rc;
+        CK(cudaEventRecord(h->ev[3], h->stream));
+        if ((rc = exchange(h, h->GF, (size_t)h->F * h->Kp))) return rc;
+        CK(cudaEventRecord(h->ev[4], h->stream));
+        if (checklb && (rc = tp_log_correction(h, 0, h->scal + SC_SUMLOGD))) return rc;
+    } else {
     // Dirichlet-side statistic: owner = rows, reduce over the local columns, then
     // the one exchange step, then n_total = A (.) G_F
     if ((rc = run_pass(h, 1, checklb ? h->scal + SC_SUMLOGD : nullptr))) return rc;
@@ -601,6 +627,7 @@ extern "C" int nbmf_vb_step(nbmf_handle *h, int checklb)
     // Beta-side statistics: owner = (column, branch) lanes, all local
     if ((rc = run_pass(h, 0, nullptr))) return rc;
     if (checklb && use_tensor_path(h) && (rc = tp_log_correction(h, 0, h->scal + SC_SUMLOGD))) return rc;
+    }
     if (use_tensor_path(h)) {
         if ((rc = tp_finalize(h))) return rc;
     } else {
@@ -690,6 +717,62 @@ extern "C" int nbmf_vb_aspect(nbmf_handle *h, int K, double alpha, double beta, 
     for (int i = 0; i < iter; i++)
         if ((rc = nbmf_vb_step(h, checklb))) { h->vb_active = false; return rc; }
     return nbmf_vb_end(h, E_W, E_H, lowerbounds, iter, E_Z);
+}
+
+// VB_Aspect_Rcpp with V given as host bit planes and the initial statistics as host arrays: one
+// call = upload + iter iterations + results.  The upload is cut into column blocks on a copy
+// stream and the first iteration consumes the blocks as they land (both passes of a block need
+// nothing but that block's columns), so the PCIe transfer overlaps the contraction.
+extern "C" int nbmf_vb_aspect_bits(nbmf_handle *h, const uint32_t *vbits, int64_t F, int64_t N, int K,
+                                   double alpha, double beta, double gamma, int iter, int checklb,
+                                   const double *n_total, const double *f_ones, const double *f_zeros,
+                                   double *E_W, double *E_H, double *lowerbounds)
+{
+    if (!h) return NBMF_ERR_ARG;
+    if (!vbits || F <= 0 || N <= 0 || iter < 0) return fail(h, NBMF_ERR_ARG, "nbmf_vb_aspect_bits: bad arguments");
+    CK(cudaSetDevice(h->device));
+    // block size: whole rows-pass chunks (512 steps x 32 columns); at most 32 blocks
+    int64_t blk = h->opts.pipe_block_cols > 0 ? (int64_t)h->opts.pipe_block_cols : 32768;
+    blk = std::max<int64_t>(64, (blk + 63) / 64 * 64);
+    while ((N + blk - 1) / blk > 32) blk *= 2;
+    const int nb = (int)((N + blk - 1) / blk);
+    int rc = alloc_planes(h, F, N);
+    if (rc) return rc;
+    h->has_na = false; h->nobs = F * N;
+    const bool pipelined = iter >= 1 && nb >= 2 && use_tensor_path(h);
+    if (!pipelined) {
+        if ((rc = nbmf_set_data_bits(h, vbits, nullptr, F, N))) return rc;
+        if ((rc = nbmf_set_stats(h, K, n_total, f_ones, f_zeros))) return rc;
+        return nbmf_vb_aspect(h, K, alpha, beta, gamma, iter, checklb, E_W, E_H, lowerbounds, nullptr);
+    }
+    tp_invalidate_data(h);
+    if (!h->copy_stream) CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (int b = 0; b <= nb; b++) h->pipe_n0[b] = std::min<int64_t>(N, (int64_t)b * blk);
+    // the statistics first (the parameters of the first iteration need all of them), then V
+    if ((rc = nbmf_set_stats(h, K, n_total, f_ones, f_zeros))) return rc;   // synchronises h->stream
+    const int64_t fw_in = (F + 31) / 32;
+    for (int b = 0; b < nb; b++) {
+        const int64_t c0 = h->pipe_n0[b], c1 = h->pipe_n0[b + 1];
+        if (!h->pipe_ev[b]) CK(cudaEventCreateWithFlags(&h->pipe_ev[b], cudaEventDisableTiming));
+        CK(cudaMemcpy2DAsync(h->vc + c0 * h->Fw, (size_t)h->Fw * 4, vbits + c0 * fw_in, (size_t)fw_in * 4,
+                             (size_t)fw_in * 4, (size_t)(c1 - c0), cudaMemcpyHostToDevice, h->copy_stream));
+        CK(cudaEventRecord(h->pipe_ev[b], h->copy_stream));
+    }
+    fill_mask_kernel<<<nblk(N * h->Fw, 256), 256, 0, h->stream>>>(h->mc, N, h->Fw, F);
+    LAUNCH_CHECK();
+    fill_mask_kernel<<<nblk(F * h->Nw, 256), 256, 0, h->stream>>>(h->mr, F, h->Nw, N);
+    LAUNCH_CHECK();
+    if ((rc = nbmf_vb_begin(h, K, alpha, beta, gamma, 0))) { cudaStreamSynchronize(h->copy_stream); return rc; }
+    h->pipe_blocks = nb;
+    for (int i = 0; i < iter; i++)
+        if ((rc = nbmf_vb_step(h, checklb))) {
+            h->vb_active = false; h->pipe_blocks = 0;
+            cudaStreamSynchronize(h->copy_stream);   // the host buffer must not be in use after the return
+            return rc;
+        }
+    rc = nbmf_vb_end(h, E_W, E_H, lowerbounds, iter, nullptr);
+    cudaStreamSynchronize(h->copy_stream);
+    return rc;
 }
 
 extern "C" int nbmf_vb_argmax_labels(nbmf_handle *h, int32_t *Z_out)

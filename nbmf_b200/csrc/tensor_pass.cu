@@ -46,6 +46,7 @@ struct TPState {
     __half *A_hi = nullptr, *A_lo = nullptr;   // [Fpad][KP]
     __half *B_hi = nullptr, *B_lo = nullptr;   // [N2pad][KP]
     float *partial = nullptr; size_t partial_bytes = 0;
+    float *partial2 = nullptr; size_t partial2_bytes = 0;   // cols-pass partials of the pipelined step
     CUtensorMap tmA, tmB, tmAlo, tmBlo;
     unsigned long long *dmax = nullptr;   // [0] max A bits, [1] max BB bits
     int *dexp = nullptr;                  // [0] eA, [1] eB
@@ -92,7 +93,7 @@ void tp_free(nbmf_handle *h)
     TPState *s = (TPState *)h->tp;
     if (!s) return;
     cudaFree(s->A_hi); cudaFree(s->A_lo); cudaFree(s->B_hi); cudaFree(s->B_lo);
-    cudaFree(s->partial); cudaFree(s->dmax); cudaFree(s->dexp); cudaFree(s->dacc); cudaFree(s->derr);
+    cudaFree(s->partial); cudaFree(s->partial2); cudaFree(s->dmax); cudaFree(s->dexp); cudaFree(s->dacc); cudaFree(s->derr);
     cudaFree(s->cntF); cudaFree(s->cntN);
     delete s;
     h->tp = nullptr;
@@ -488,10 +489,13 @@ struct TPArgs {
     const uint32_t *vbits, *mbits; // [owner_rows][words] packed along the streamed index
     int64_t words;
     int64_t L;                     // owner lanes
-    int64_t owner_tiles;           // ceil(L/128)
-    int64_t stream_steps;          // total steps of 64 streamed rows
-    int chunk_steps, n_chunks;
-    float *partial;                // [n_chunks][owner_tiles*128][KP]
+    // One launch covers owner tiles [tile_begin, tile_begin + owner_tiles) x streamed steps
+    // [step_begin, step_end) cut into n_chunks chunks of chunk_steps (the whole problem, or one
+    // column block of a pipelined upload).
+    int64_t owner_tiles, tile_begin, owner_tiles_total;
+    int64_t step_begin, step_end;  // steps of 64 streamed rows
+    int chunk_steps, n_chunks, chunk_base;
+    float *partial;                // [chunks of all launches][owner_tiles_total*128][KP]
     const int *dexp;               // eA, eB
     double *dacc;                  // [0] += sum log2 S over selected entries (rows pass only)
     int *derr;
@@ -588,8 +592,8 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
             PROF_DECL;
             for (int64_t w = blockIdx.x; w < n_items; w += gridDim.x) {
                 const int chunk = (int)(w / a.owner_tiles);
-                const int64_t t0 = (int64_t)chunk * a.chunk_steps;
-                const int nst = (int)min((int64_t)a.chunk_steps, a.stream_steps - t0);
+                const int64_t t0 = a.step_begin + (int64_t)chunk * a.chunk_steps;
+                const int nst = (int)min((int64_t)a.chunk_steps, a.step_end - t0);
                 uint32_t pre = 0;
                 for (int t = 0; t < nst; t++) {
                     if (!pre && !mbar_wait(BAR_EMPTY(stage), phase ^ 1, abort_flag, 1)) break;
@@ -633,8 +637,8 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
             PROF_DECL;
             for (int64_t w = blockIdx.x; w < n_items; w += gridDim.x) {
                 const int chunk = (int)(w / a.owner_tiles);
-                const int64_t t0 = (int64_t)chunk * a.chunk_steps;
-                const int nst = (int)min((int64_t)a.chunk_steps, a.stream_steps - t0);
+                const int64_t t0 = a.step_begin + (int64_t)chunk * a.chunk_steps;
+                const int nst = (int)min((int64_t)a.chunk_steps, a.step_end - t0);
                 if (!mbar_wait(BAR_UREADY, u_phase, abort_flag, 2)) break;
                 u_phase ^= 1;
                 bool ok = true;
@@ -682,8 +686,8 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
             PROF_DECL;
             for (int64_t w = blockIdx.x; w < n_items; w += gridDim.x) {
                 const int chunk = (int)(w / a.owner_tiles);
-                const int64_t t0 = (int64_t)chunk * a.chunk_steps;
-                const int nst = (int)min((int64_t)a.chunk_steps, a.stream_steps - t0);
+                const int64_t t0 = a.step_begin + (int64_t)chunk * a.chunk_steps;
+                const int nst = (int)min((int64_t)a.chunk_steps, a.step_end - t0);
                 // G of the previous item has been drained (the epilogue arrives after the drain)
                 if (!mbar_wait(BAR_UREADY, u_phase, abort_flag, 6)) break;
                 u_phase ^= 1;
@@ -747,9 +751,9 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
         constexpr int NDRAIN = KP / GCOLS;                   // groups that take part (4 or 2)
         auto drain_G = [&](int64_t pw) {
             if (grp < NDRAIN) {
-                const int pchunk = (int)(pw / a.owner_tiles);
-                const int64_t ptile = pw % a.owner_tiles;
-                float *dst = a.partial + (((int64_t)pchunk * a.owner_tiles + ptile) * 128 + lrow) * KP + grp * GCOLS;
+                const int pchunk = a.chunk_base + (int)(pw / a.owner_tiles);
+                const int64_t ptile = a.tile_begin + pw % a.owner_tiles;
+                float *dst = a.partial + (((int64_t)pchunk * a.owner_tiles_total + ptile) * 128 + lrow) * KP + grp * GCOLS;
                 uint32_t r[32];
                 tc_ld32(tmem + lane_addr + C::COL_G + grp * GCOLS, r);
                 tc_wait_ld();
@@ -760,9 +764,9 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
         };
         for (int64_t w = blockIdx.x; w < n_items && ok; w += gridDim.x) {
             const int chunk = (int)(w / a.owner_tiles);
-            const int64_t tile = w % a.owner_tiles;
-            const int64_t t0 = (int64_t)chunk * a.chunk_steps;
-            const int nst = (int)min((int64_t)a.chunk_steps, a.stream_steps - t0);
+            const int64_t tile = a.tile_begin + w % a.owner_tiles;
+            const int64_t t0 = a.step_begin + (int64_t)chunk * a.chunk_steps;
+            const int nst = (int)min((int64_t)a.chunk_steps, a.step_end - t0);
             const int64_t l = tile * 128 + lrow;
             const bool lane_ok = l < a.L;
             // ---- owner operand of this item: issue the global loads before waiting for the
@@ -959,12 +963,19 @@ static cudaError_t launch_tp(const CUtensorMap &tm, const CUtensorMap &tmlo, con
 
 static float *g_tp_dbg = nullptr; // set by nbmf_debug_tp_dump only
 
-int tp_pass(nbmf_handle *h, int owner_rows, double *sumlogD)
+// chunk length: long chunks amortise the per-item drain / operand reload (C5: 64 -> 167 ms,
+// 128 -> 154, 512 -> 141 ms per iteration), but there must be enough items for every SM
+static int tp_chunk_steps(const nbmf_handle *h, const TPState *s, int64_t owner_tiles, int64_t steps)
 {
-    TPState *s = (TPState *)h->tp;
-    if (!s) { h->err = "tp_pass before tp_prepare"; return NBMF_ERR_STATE; }
-    const int KP = s->KP;
-    TPArgs a{};
+    const int64_t min_chunks = std::max<int64_t>(1, (4 * (int64_t)h->sm_count + owner_tiles - 1) / owner_tiles);
+    int64_t cs = (steps + min_chunks - 1) / min_chunks;
+    cs = std::max<int64_t>(std::min<int64_t>(cs, s->chunk_steps), std::min<int64_t>(16, steps));
+    return (int)std::min<int64_t>(cs, steps);
+}
+
+// everything of a pass that does not depend on the sub-range a launch covers
+static void tp_base_args(nbmf_handle *h, TPState *s, int owner_rows, bool want_log, TPArgs &a, int64_t &stream_steps)
+{
     int64_t S_rows;
     if (owner_rows) {
         a.U_hi = s->A_hi; a.vbits = h->vr; a.mbits = h->mr; a.words = h->Nw;
@@ -973,45 +984,40 @@ int tp_pass(nbmf_handle *h, int owner_rows, double *sumlogD)
         a.U_hi = s->B_hi; a.vbits = h->vc; a.mbits = h->mc; a.words = h->Fw;
         a.L = 2 * h->N; S_rows = h->F;
     }
-    a.owner_tiles = (a.L + 127) / 128;
-    a.stream_steps = (S_rows + 63) / 64;
-    // chunk length: long chunks amortise the per-item drain / operand reload (C5: 64 -> 167 ms,
-    // 128 -> 154, 512 -> 141 ms per iteration), but there must be enough items for every SM
-    {
-        const int64_t min_chunks = std::max<int64_t>(1, (4 * (int64_t)h->sm_count + a.owner_tiles - 1) / a.owner_tiles);
-        int64_t cs = (a.stream_steps + min_chunks - 1) / min_chunks;
-        cs = std::max<int64_t>(std::min<int64_t>(cs, s->chunk_steps), std::min<int64_t>(16, a.stream_steps));
-        a.chunk_steps = (int)std::min<int64_t>(cs, a.stream_steps);
-    }
-    a.n_chunks = (int)((a.stream_steps + a.chunk_steps - 1) / a.chunk_steps);
-    const int64_t Lpad = a.owner_tiles * 128;
-    size_t need = (size_t)a.n_chunks * Lpad * KP * 4;
-    if (need > s->partial_bytes) {
-        cudaFree(s->partial); s->partial = nullptr; s->partial_bytes = 0;
-        if (cudaMalloc(&s->partial, need) != cudaSuccess) {
-            cudaGetLastError();
-            h->err = "tensor path: partial buffer allocation failed";
-            return NBMF_ERR_OOM;
-        }
-        s->partial_bytes = need;
-    }
-    a.partial = s->partial;
+    a.owner_tiles_total = (a.L + 127) / 128;
+    stream_steps = (S_rows + 63) / 64;
     a.dexp = s->dexp; a.dacc = s->dacc; a.derr = s->derr;
-    a.want_log = (sumlogD != nullptr);
+    a.want_log = want_log;
     // AUTO: the W_lo term of stage 2 buys ~5x accuracy at 10^3..10^4 rows/columns, but its benefit
     // falls like 1/sqrt(reduction length): at 262144^2 hi-only is within 1.6x of hi+lo and both are
     // ~1e-6 of the FP64 path (profiles/r1_error_growth_c5.log), so it is dropped there.
-    {
-        const int64_t n_glob = h->opts.n_global > 0 ? h->opts.n_global : h->N;
-        if (h->opts.precision == NBMF_PREC_TENSOR) a.use_lo = 1;
-        else if (h->opts.precision == NBMF_PREC_TENSOR_FAST) a.use_lo = 0;
-        else a.use_lo = (std::min<int64_t>(h->F, n_glob) < 131072) ? 1 : 0;
-        h->timing.path = a.use_lo ? 1 : 2;
-    }
+    const int64_t n_glob = h->opts.n_global > 0 ? h->opts.n_global : h->N;
+    if (h->opts.precision == NBMF_PREC_TENSOR) a.use_lo = 1;
+    else if (h->opts.precision == NBMF_PREC_TENSOR_FAST) a.use_lo = 0;
+    else a.use_lo = (std::min<int64_t>(h->F, n_glob) < 131072) ? 1 : 0;
+    h->timing.path = a.use_lo ? 1 : 2;
     a.dbg = g_tp_dbg;
     { const char *f = getenv("NBMF_TP_DEBUG_FLAGS"); a.dbg_flags = f ? atoi(f) : 0; }
-    if (a.want_log) cudaMemsetAsync(s->dacc, 0, 16, h->stream);
+}
+
+static int tp_ensure_partial(nbmf_handle *h, float **buf, size_t *have, size_t need)
+{
+    if (need <= *have) return NBMF_OK;
+    cudaFree(*buf); *buf = nullptr; *have = 0;
+    if (cudaMalloc(buf, need) != cudaSuccess) {
+        cudaGetLastError();
+        h->err = "tensor path: partial buffer allocation failed";
+        return NBMF_ERR_OOM;
+    }
+    *have = need;
+    return NBMF_OK;
+}
+
+static int tp_launch(nbmf_handle *h, TPState *s, int owner_rows, const TPArgs &a)
+{
+    const int KP = s->KP;
     const int64_t items = (int64_t)a.n_chunks * a.owner_tiles;
+    if (items <= 0) return NBMF_OK;
     const int grid = (int)std::min<int64_t>(items, h->sm_count);
     // the mask plane is skipped only when there is no NA and no padding anywhere (padded lanes /
     // streamed rows rely on the mask bits being zero)
@@ -1027,13 +1033,90 @@ int tp_pass(nbmf_handle *h, int owner_rows, double *sumlogD)
         else e = launch_tp<64, true, false>(s->tmB, s->tmBlo, a, grid, h->stream, use_mask);
     }
     if (e != cudaSuccess) { h->err = std::string("tp_pass launch: ") + cudaGetErrorString(e); return NBMF_ERR_CUDA; }
-    tp_reduce_kernel<<<(unsigned)((a.L * KP + 255) / 256), 256, 0, h->stream>>>(s->partial, a.n_chunks, Lpad, a.L, KP, s->dexp,
-                                                                              owner_rows ? 1 : 0, owner_rows ? h->GF : h->GN);
-    if (a.want_log) tp_logfix_kernel<<<1, 32, 0, h->stream>>>(s->dacc, s->dexp, (double)h->nobs, sumlogD);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) { h->err = std::string("tp_pass reduce: ") + cudaGetErrorString(e); return NBMF_ERR_CUDA; }
-    h->timing.launches += 2 + (a.want_log ? 1 : 0);
+    h->timing.launches += 1;
     return NBMF_OK;
+}
+
+static int tp_reduce(nbmf_handle *h, TPState *s, int owner_rows, const float *partial, int n_chunks, int64_t L,
+                     int64_t owner_tiles_total, bool want_log, double *sumlogD)
+{
+    const int KP = s->KP;
+    tp_reduce_kernel<<<(unsigned)((L * KP + 255) / 256), 256, 0, h->stream>>>(partial, n_chunks, owner_tiles_total * 128, L, KP, s->dexp,
+                                                                            owner_rows ? 1 : 0, owner_rows ? h->GF : h->GN);
+    if (want_log) tp_logfix_kernel<<<1, 32, 0, h->stream>>>(s->dacc, s->dexp, (double)h->nobs, sumlogD);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { h->err = std::string("tp_pass reduce: ") + cudaGetErrorString(e); return NBMF_ERR_CUDA; }
+    h->timing.launches += 1 + (want_log ? 1 : 0);
+    return NBMF_OK;
+}
+
+int tp_pass(nbmf_handle *h, int owner_rows, double *sumlogD)
+{
+    TPState *s = (TPState *)h->tp;
+    if (!s) { h->err = "tp_pass before tp_prepare"; return NBMF_ERR_STATE; }
+    TPArgs a{};
+    int64_t stream_steps;
+    tp_base_args(h, s, owner_rows, sumlogD != nullptr, a, stream_steps);
+    a.owner_tiles = a.owner_tiles_total; a.tile_begin = 0;
+    a.step_begin = 0; a.step_end = stream_steps;
+    a.chunk_steps = tp_chunk_steps(h, s, a.owner_tiles, stream_steps);
+    a.n_chunks = (int)((stream_steps + a.chunk_steps - 1) / a.chunk_steps);
+    a.chunk_base = 0;
+    int rc = tp_ensure_partial(h, &s->partial, &s->partial_bytes, (size_t)a.n_chunks * a.owner_tiles_total * 128 * s->KP * 4);
+    if (rc) return rc;
+    a.partial = s->partial;
+    if (a.want_log) cudaMemsetAsync(s->dacc, 0, 16, h->stream);
+    if ((rc = tp_launch(h, s, owner_rows, a))) return rc;
+    return tp_reduce(h, s, owner_rows, s->partial, a.n_chunks, a.L, a.owner_tiles_total, a.want_log, sumlogD);
+}
+
+// Both passes of one VB iteration, launched column block by column block as the blocks of a
+// pipelined upload arrive (nbmf_vb_aspect_bits).  Block b = columns [n0[b], n0[b+1]); before its
+// launches the stream waits for ev[b] and builds the block's part of the row-packed plane
+// (prepare_block).  The two statistics are independent given the parameters, so the rows pass
+// (streamed chunks = the block's columns) and the cols pass (owner tiles = the block's columns)
+// of a block run back to back; the reductions over chunks follow once at the end.
+int tp_passes_pipelined(nbmf_handle *h, int n_blocks, const int64_t *n0, cudaEvent_t *ev,
+                        int (*prepare_block)(nbmf_handle *, int64_t, int64_t), double *sumlogD)
+{
+    TPState *s = (TPState *)h->tp;
+    if (!s) { h->err = "tp_passes_pipelined before tp_prepare"; return NBMF_ERR_STATE; }
+    const int KP = s->KP;
+    TPArgs ar{}, ac{};
+    int64_t steps_r, steps_c;
+    tp_base_args(h, s, 1, sumlogD != nullptr, ar, steps_r);
+    tp_base_args(h, s, 0, false, ac, steps_c);
+    // rows pass: a block's columns are 2 streamed rows each -> 32 columns per step
+    const int64_t blk_cols = n0[1] - n0[0];
+    const int cs_r = tp_chunk_steps(h, s, ar.owner_tiles_total, blk_cols / 32);
+    int chunks_r_total = 0;
+    for (int b = 0; b < n_blocks; b++) chunks_r_total += (int)(((n0[b + 1] - n0[b] + 31) / 32 + cs_r - 1) / cs_r);
+    // cols pass: a block's columns are 2 owner lanes each -> 64 columns per owner tile
+    const int cs_c = tp_chunk_steps(h, s, std::max<int64_t>(1, blk_cols / 64), steps_c);
+    const int chunks_c = (int)((steps_c + cs_c - 1) / cs_c);
+    int rc;
+    if ((rc = tp_ensure_partial(h, &s->partial, &s->partial_bytes, (size_t)chunks_r_total * ar.owner_tiles_total * 128 * KP * 4))) return rc;
+    if ((rc = tp_ensure_partial(h, &s->partial2, &s->partial2_bytes, (size_t)chunks_c * ac.owner_tiles_total * 128 * KP * 4))) return rc;
+    ar.partial = s->partial; ac.partial = s->partial2;
+    if (ar.want_log) cudaMemsetAsync(s->dacc, 0, 16, h->stream);
+    int chunk_base = 0;
+    for (int b = 0; b < n_blocks; b++) {
+        const int64_t c0 = n0[b], c1 = n0[b + 1];
+        if (cudaStreamWaitEvent(h->stream, ev[b], 0) != cudaSuccess) { h->err = "cudaStreamWaitEvent failed"; return NBMF_ERR_CUDA; }
+        if ((rc = prepare_block(h, c0, c1))) return rc;
+        ar.owner_tiles = ar.owner_tiles_total; ar.tile_begin = 0;
+        ar.step_begin = c0 / 32; ar.step_end = (c1 + 31) / 32;
+        ar.chunk_steps = cs_r;
+        ar.n_chunks = (int)((ar.step_end - ar.step_begin + cs_r - 1) / cs_r);
+        ar.chunk_base = chunk_base; chunk_base += ar.n_chunks;
+        if ((rc = tp_launch(h, s, 1, ar))) return rc;
+        ac.tile_begin = c0 / 64; ac.owner_tiles = (c1 + 63) / 64 - c0 / 64;
+        ac.step_begin = 0; ac.step_end = steps_c;
+        ac.chunk_steps = cs_c; ac.n_chunks = chunks_c; ac.chunk_base = 0;
+        if ((rc = tp_launch(h, s, 0, ac))) return rc;
+    }
+    if ((rc = tp_reduce(h, s, 1, s->partial, chunks_r_total, ar.L, ar.owner_tiles_total, ar.want_log, sumlogD))) return rc;
+    return tp_reduce(h, s, 0, s->partial2, chunks_c, ac.L, ac.owner_tiles_total, false, nullptr);
 }
 
 int tp_check_error(nbmf_handle *h)

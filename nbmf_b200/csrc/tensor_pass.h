@@ -7,6 +7,9 @@ bool tp_supported(const nbmf_handle *h);      // K, sizes and device fit the ten
 int tp_prepare(nbmf_handle *h);               // allocate f16 operand buffers + tensor maps
 int tp_convert_operands(nbmf_handle *h);      // A, BB (fp64) -> scaled f16 hi/lo
 int tp_pass(nbmf_handle *h, int owner_rows, double *sumlogD);
+// both passes, column block by column block behind the events of a pipelined upload
+int tp_passes_pipelined(nbmf_handle *h, int n_blocks, const int64_t *n0, cudaEvent_t *ev,
+                        int (*prepare_block)(nbmf_handle *, int64_t, int64_t), double *sumlogD);
 int tp_log_correction(nbmf_handle *h, int owner_rows, double *sumlogD); // call after each pass, before the exchange
 int tp_finalize(nbmf_handle *h);            // statistics = U (.) G with exact-count row normalisation
 void tp_invalidate_data(nbmf_handle *h);     // V changed under the same shape: recount on next use
