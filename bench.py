@@ -262,12 +262,12 @@ def main():
         ach = flops / (pass_ms * 1e-3) / 1e12 if pass_ms > 0 else 0.0
         peak = peaks["bf16_sustained"]
         # DRAM bytes of the two contraction launches of one iteration, from the committed ncu capture of
-        # this very command (profiles/r1_launches_c5.txt): rows 9.84+2.13 GB, cols 9.76+2.13 GB
-        traffic = 23.86e9 if (args.workload == "c5" and world == 1 and int(tim["path"]) == 2) else None
+        # this very command (profiles/r1_launches_c5.txt): rows 9.82+2.13 GB, cols 9.75+2.13 GB
+        traffic = 23.83e9 if (args.workload == "c5" and world == 1 and int(tim["path"]) == 2) else None
         roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                 "traffic": traffic,
                 "traffic_note": "sum over the rows-pass and cols-pass launches of one iteration (ncu dram__bytes_read+write, "
-                                "profiles/r1_launches_c5.txt); algorithmic: V bit plane 2 x 8.6 GB + operands 0.5 GB + chunk partials 4.3 GB", "peak_source": f"{peaks['source']} bf16 sustained (MEASURED_PEAKS.json)",
+                                "profiles/r1_launches_c5.txt); algorithmic: V bit plane 2 x 8.6 GB + operands 0.5 GB + chunk partials 4.3 GB write, 4.3 GB read back by the reductions", "peak_source": f"{peaks['source']} bf16 sustained (MEASURED_PEAKS.json)",
                 "kernel": "contraction passes (rows + cols) of one iteration, CUDA events inside libnbmf_cuda",
                 "pass_rows_ms": tim["pass_rows_ms"], "pass_cols_ms": tim["pass_cols_ms"],
                 "params_ms": tim["params_ms"], "exchange_ms": tim["exchange_ms"],

@@ -64,7 +64,7 @@ typedef struct nbmf_opts {
     int device;          /* CUDA ordinal                                                    */
     int precision;       /* nbmf_precision                                                  */
     int flush_interval;  /* tensor path: steps between TMEM accumulator flushes; 0 = default */
-    int pipe_block_cols; /* nbmf_vb_aspect_bits: columns per upload block; 0 = default (32768)  */
+    int pipe_block_cols; /* nbmf_vb_aspect_bits: columns per upload block; 0 = about N/8         */
     int64_t n_global;    /* column sharding: total number of columns (0 = not sharded)      */
     int64_t n_offset;    /* first global column this handle owns                            */
 } nbmf_opts;

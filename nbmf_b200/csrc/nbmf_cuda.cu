@@ -731,8 +731,10 @@ extern "C" int nbmf_vb_aspect_bits(nbmf_handle *h, const uint32_t *vbits, int64_
     if (!h) return NBMF_ERR_ARG;
     if (!vbits || F <= 0 || N <= 0 || iter < 0) return fail(h, NBMF_ERR_ARG, "nbmf_vb_aspect_bits: bad arguments");
     CK(cudaSetDevice(h->device));
-    // block size: whole rows-pass chunks (512 steps x 32 columns); at most 32 blocks
-    int64_t blk = h->opts.pipe_block_cols > 0 ? (int64_t)h->opts.pipe_block_cols : 32768;
+    // block size: about N/8 columns (a multiple of 64 = one owner tile of the cols pass = two
+    // steps of the rows pass); at most 32 blocks
+    int64_t blk = h->opts.pipe_block_cols > 0 ? (int64_t)h->opts.pipe_block_cols
+                                              : std::max<int64_t>(2048, ((N + 7) / 8 + 2047) / 2048 * 2048);
     blk = std::max<int64_t>(64, (blk + 63) / 64 * 64);
     while ((N + blk - 1) / blk > 32) blk *= 2;
     const int nb = (int)((N + blk - 1) / blk);
