@@ -193,6 +193,21 @@ int nbmf_gibbs_dirber(nbmf_handle *h, int K, double alpha, double beta, double g
                       double burnin, uint64_t seed, double *E_W, double *E_H,
                       const int64_t *test_idx, int64_t n_test, double *E_V_test, int32_t *Z_last);
 
+/* ---- Gibbs_DirBer_finite_Rcpp with its own (collapsed) schedule -------------
+ * The sequential sweep of collapsed_gibbs_z.cpp:392-427 run as an anti-diagonal
+ * wavefront (entries on a diagonal touch disjoint count rows, and the order of
+ * every conflicting pair is the reference's).  R's global stream is replaced by
+ * a uniform keyed (seed; f, n, sweep), so the result does not depend on the
+ * traversal order: labels and Z_samples equal the reference loop run with the
+ * same key bit for bit (oracle_gibbs_dirber_finite_keyed).  Needs the labels
+ * (nbmf_init_from_labels with Kc = K).  Z_samples: F x N x (iter -
+ * floor(iter*burnin)) int32, zero-filled, slices written as in :423-426, or
+ * NULL; Z_last F x N or NULL.  Replicas only; sized for configs the reference
+ * can run (labels and Z_samples live on the device).                          */
+int nbmf_gibbs_dirber_collapsed(nbmf_handle *h, int K, double alpha, double beta, double gamma, int iter,
+                                double burnin, uint64_t seed, int32_t *Z_samples, int *n_samples_written,
+                                int32_t *Z_last);
+
 /* one column's sweep given a fixed dictionary (sample_gibbs.cpp:22-80,
  * R sample_gibbs_ZH): v_n[F] in {0,1}, W F x K (paper orientation: Beta means),
  * returns the mean one-hot assignment C_mean F x K over kept sweeps.          */

@@ -253,6 +253,16 @@ class Engine:
                                             _ptr(E_H, _dp), _ptr(idx, _lp), nt, _ptr(E_V, _dp), _ptr(Z, _ip)))
         return E_W, E_H, (E_V[:nt] if nt else None), Z
 
+    def gibbs_dirber_collapsed(self, K, alpha=1.0, beta=1.0, gamma=1.0, iter=100, burnin=0.5, seed=1, want_samples=True):
+        """The reference's own collapsed sweep (wavefront order, uniforms keyed by entry and sweep)."""
+        ns = iter - int(np.floor(iter * burnin))
+        Zs = np.zeros((self.F, self.N, max(ns, 1)), dtype=np.int32, order="F") if want_samples else None
+        Zl = np.zeros((self.F, self.N), dtype=np.int32, order="F")
+        nw = C.c_int(0)
+        self._ck(self.lib.nbmf_gibbs_dirber_collapsed(self.h, K, alpha, beta, gamma, iter, burnin, seed, _ptr(Zs, _ip),
+                                                      C.byref(nw), _ptr(Zl, _ip)))
+        return (Zs[:, :, :ns] if want_samples else None), nw.value, Zl
+
     def gibbs_sweep_given_W(self, v_n, W, alpha=1.0, iter=100, burnin=0.5, seed=1):
         v = np.ascontiguousarray(v_n, dtype=np.int32)
         W = np.asfortranarray(W, dtype=np.float64)
@@ -318,12 +328,23 @@ def VB_DirBer_Rcpp(V, Z, K, alpha=1.0, beta=1.0, gamma=1.0, iter=100, *, engine=
 
 
 def Gibbs_DirBer_finite_Rcpp(V, Z, K, alpha=1.0, beta=1.0, gamma=1.0, iter=100, burnin=0.5, *, seed=1,
-                             test_idx=None, engine=None, device=0):
-    """collapsed_gibbs_z.cpp:363-437.  The engine runs the uncollapsed blocked chain
+                             test_idx=None, engine=None, device=0, collapsed=False):
+    """collapsed_gibbs_z.cpp:363-437.  By default the engine runs the uncollapsed blocked chain
     (same stationary posterior); instead of the F x N x J `Z_samples` cube it
     returns the Rao-Blackwell means the R wrapper derives from it
-    (generic_Gibbs_DirBer.R:19-20,54-101) plus the last assignment."""
+    (generic_Gibbs_DirBer.R:19-20,54-101) plus the last assignment.
+    `collapsed=True` runs the reference's own sweep (wavefront order, keyed uniforms) and
+    returns the reference's `Z_samples` (F x N x J int; its `E_Z` is a function of it,
+    compute_expectation_Z :157-173) plus the last assignment."""
     e, own = _engine_for(V, engine, device=device, precision=_lib.PREC_FP64)
+    if collapsed:
+        try:
+            e.init_from_labels(Z, K)
+            Zs, nw, Zl = e.gibbs_dirber_collapsed(K, alpha, beta, gamma, iter, burnin, seed)
+        finally:
+            if own:
+                e.close()
+        return {"Z_samples": Zs, "Z_last": Zl, "written": nw}
     try:
         e.init_from_labels(Z, K)
         E_W, E_H, E_V, Zl = e.gibbs_dirber(K, alpha, beta, gamma, iter, burnin, seed, test_idx, want_Z=True)

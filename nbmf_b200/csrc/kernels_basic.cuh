@@ -542,6 +542,89 @@ __global__ void __launch_bounds__(1024) cvb0_wavefront_kernel(WaveArgs a)
     }
 }
 
+// ---------------------------------------------------------------------------
+// Collapsed Gibbs sweep of Gibbs_DirBer_finite_Rcpp (collapsed_gibbs_z.cpp:392-421) in the
+// same anti-diagonal wavefront order as the CVB0 kernel above: an entry reads and writes only
+// the count rows of its own f and n, so ordering by d = f + n keeps every conflicting pair in
+// the reference's column-major order.  The reference draws from R's global stream
+// (rmultinom, :411); here the uniform of entry (f, n) in sweep i is Philox4x32-10 keyed
+// (seed; f, n, i), which makes the chain independent of the traversal order -- the oracle
+// restates the reference loop with the same key, and the labels agree bit for bit.
+// Integer counts; the probabilities follow :402-408 in fp64 without FMA contraction.
+// ---------------------------------------------------------------------------
+struct GibbsWaveArgs {
+    const uint32_t *vc, *mc;
+    int64_t F, N, Fw;
+    int K, iter, nburnin, nsamples;
+    double alpha, beta, gamma;
+    uint64_t seed;
+    int32_t *Z;          // [N][F] = f + F n, updated in place
+    int32_t *cF;         // [F][K]      n_total
+    int32_t *cN;         // [2N][K]     row 2n+1 f_ones, row 2n f_zeros
+    int32_t *Z_samples;  // [nsamples][N][F] or NULL (:423-426)
+    int *n_written;
+};
+
+template <bool SINGLE_BLOCK>
+__global__ void __launch_bounds__(1024) gibbs_collapsed_wavefront_kernel(GibbsWaveArgs a)
+{
+    cg::grid_group grid = cg::this_grid();
+    const int64_t F = a.F, N = a.N;
+    const int K = a.K;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    int j = 0;
+    for (int i = 1; i < a.iter; i++) {   // :392
+        for (int64_t d = 0; d <= F + N - 2; d++) {
+            const int64_t f_lo = d - (N - 1) > 0 ? d - (N - 1) : 0;
+            const int64_t f_hi = d < F - 1 ? d : F - 1;
+            for (int64_t f = f_lo + tid; f <= f_hi; f += nthreads) {
+                const int64_t n = d - f;
+                const uint32_t mw = a.mc ? a.mc[n * a.Fw + (f >> 5)] : 0xffffffffu;
+                if (!((mw >> (f & 31)) & 1u)) continue;
+                const int v = (a.vc[n * a.Fw + (f >> 5)] >> (f & 31)) & 1u;
+                int32_t *nF = a.cF + f * K, *nV = a.cN + (2 * n + v) * K;
+                const int32_t *n1 = a.cN + (2 * n + 1) * K, *n0 = a.cN + (2 * n) * K;
+                const int k0 = a.Z[f + F * n];
+                nF[k0] -= 1; nV[k0] -= 1;   // remove_assignment (:75-85)
+                double s = 0.0;
+                for (int k = 0; k < K; k++) {   // :402-407
+                    const double gp = __dadd_rn(a.gamma, (double)nF[k]);
+                    const double ap = __dadd_rn(a.alpha, (double)n1[k]);
+                    const double bp = __dadd_rn(a.beta, (double)n0[k]);
+                    s = __dadd_rn(s, __ddiv_rn(__dmul_rn(gp, v ? ap : bp), __dadd_rn(ap, bp)));
+                }
+                const philox4 r = philox4x32_10((uint32_t)f, (uint32_t)n, (uint32_t)i, 0u, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+                const double u = u64_to_unif(r.x, r.y);
+                double c = 0.0;
+                int k1 = -1, last_pos = K - 1;
+                for (int k = 0; k < K; k++) {   // :408, inverse CDF in place of rmultinom + index_max (:411-413)
+                    const double gp = __dadd_rn(a.gamma, (double)nF[k]);
+                    const double ap = __dadd_rn(a.alpha, (double)n1[k]);
+                    const double bp = __dadd_rn(a.beta, (double)n0[k]);
+                    const double pr = __ddiv_rn(__ddiv_rn(__dmul_rn(gp, v ? ap : bp), __dadd_rn(ap, bp)), s);
+                    c = __dadd_rn(c, pr);
+                    if (pr > 0.0) last_pos = k;
+                    if (k1 < 0 && u < c) k1 = k;
+                }
+                if (k1 < 0) k1 = last_pos;
+                a.Z[f + F * n] = k1;        // set_assignment (:63-72)
+                nF[k1] += 1; nV[k1] += 1;
+            }
+            if (SINGLE_BLOCK) __syncthreads();
+            else grid.sync();
+        }
+        if (i >= a.nburnin && a.Z_samples && j < a.nsamples) {   // :423-426
+            int32_t *dst = a.Z_samples + (int64_t)j * F * N;
+            for (int64_t e = tid; e < F * N; e += nthreads) dst[e] = a.Z[e];
+            j++;
+            if (SINGLE_BLOCK) __syncthreads();
+            else grid.sync();
+        } else if (i >= a.nburnin && j < a.nsamples) j++;
+    }
+    if (tid == 0) *a.n_written = j;
+}
+
 // one-hot E_Z [n][f][Kc] + counters from labels (commons.cpp:29-42,
 // collapsed_gibbs_z_VB.cpp:42-66); counters come from the histogram kernel.
 __global__ void onehot_ez_kernel(const int32_t *__restrict__ Z, const uint32_t *__restrict__ mc,

@@ -1053,6 +1053,88 @@ extern "C" int nbmf_gibbs_dirber(nbmf_handle *h, int K, double alpha, double bet
     return rc;
 }
 
+// Gibbs_DirBer_finite_Rcpp (collapsed_gibbs_z.cpp:363-437) with its own schedule: the collapsed
+// sweep in anti-diagonal wavefront order, uniforms keyed (seed; f, n, sweep).  Sized for the
+// configurations the reference itself can run (labels + Z_samples on the device); replicas only.
+extern "C" int nbmf_gibbs_dirber_collapsed(nbmf_handle *h, int K, double alpha, double beta, double gamma,
+                                           int iter, double burnin, uint64_t seed, int32_t *Z_samples,
+                                           int *n_samples_written, int32_t *Z_last)
+{
+    if (!h) return NBMF_ERR_ARG;
+    if (!h->vc) return fail(h, NBMF_ERR_STATE, "no data");
+    if (K <= 0 || iter < 0 || !(alpha > 0) || !(beta > 0) || !(gamma > 0) || !(burnin >= 0) || burnin > 1)
+        return fail(h, NBMF_ERR_ARG, "nbmf_gibbs_dirber_collapsed: bad arguments");
+    if (!h->Z) return fail(h, NBMF_ERR_STATE, "the collapsed sweep needs labels: call nbmf_init_from_labels(Z, K)");
+    if (h->hook) return fail(h, NBMF_ERR_UNSUPPORTED, "the collapsed wavefront sweep is replicas-only (no column sharding)");
+    CK(cudaSetDevice(h->device));
+    const int64_t F = h->F, N = h->N;
+    const int nburnin = (int)std::floor(iter * burnin);
+    const int nsamples = iter - (int)std::floor(iter * burnin);
+    const size_t slice = (size_t)F * N * 4;
+    const bool keep = Z_samples != nullptr && nsamples > 0;
+    if (keep && (double)slice * nsamples > 32e9)
+        return fail(h, NBMF_ERR_UNSUPPORTED, "Z_samples does not fit on the device: pass NULL (nbmf_gibbs_dirber returns the posterior means without it)");
+    int32_t *cF = nullptr, *cN = nullptr, *Zs = nullptr;
+    int *nw = nullptr;
+    unsigned long long *cnt = (unsigned long long *)h->scal + SC_TMP;
+    const size_t fk = (size_t)F * K, nk = (size_t)2 * N * K;
+    cudaError_t e = cudaMalloc(&cF, fk * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&cN, nk * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&nw, 4);
+    if (e == cudaSuccess && keep) e = cudaMalloc(&Zs, slice * nsamples);
+    int rc = NBMF_OK;
+    if (e == cudaSuccess) {
+        cudaMemsetAsync(cF, 0, fk * 4, h->stream); cudaMemsetAsync(cN, 0, nk * 4, h->stream);
+        cudaMemsetAsync(nw, 0, 4, h->stream); cudaMemsetAsync(cnt, 0, 16, h->stream);
+        if (keep) cudaMemsetAsync(Zs, 0, slice * nsamples, h->stream);   // :380-381
+        counts_from_labels_kernel<<<nblk(F * N, 256), 256, 0, h->stream>>>(h->Z, h->vc, h->has_na ? h->mc : nullptr, F, N, h->Fw, K, cF, cN, cnt + 1);
+        e = cudaGetLastError();
+        unsigned long long bad = 0;
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&bad, cnt + 1, 8, cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        if (e == cudaSuccess && bad) rc = fail(h, NBMF_ERR_ARG, "Z contains labels outside 0..K-1");
+    }
+    cudaEventRecord(h->ev[0], h->stream);
+    h->timing = nbmf_timing{};
+    if (e == cudaSuccess && rc == NBMF_OK && iter > 1) {
+        GibbsWaveArgs a{};
+        a.vc = h->vc; a.mc = h->has_na ? h->mc : nullptr; a.F = F; a.N = N; a.Fw = h->Fw;
+        a.K = K; a.iter = iter; a.nburnin = nburnin; a.nsamples = nsamples;
+        a.alpha = alpha; a.beta = beta; a.gamma = gamma; a.seed = seed;
+        a.Z = h->Z; a.cF = cF; a.cN = cN; a.Z_samples = keep ? Zs : nullptr; a.n_written = nw;
+        const int64_t diag = std::min(F, N);
+        if (diag <= 1024) {
+            int threads = (int)std::max<int64_t>(32, round_up64(diag, 32));
+            gibbs_collapsed_wavefront_kernel<true><<<1, threads, 0, h->stream>>>(a);
+            e = cudaGetLastError();
+        } else {
+            int threads = 256, per_sm = 0;
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gibbs_collapsed_wavefront_kernel<false>, threads, 0);
+            int blocks = (int)std::min<int64_t>((diag + threads - 1) / threads, (int64_t)per_sm * h->sm_count);
+            void *args[] = {&a};
+            if (e == cudaSuccess)
+                e = cudaLaunchCooperativeKernel((void *)gibbs_collapsed_wavefront_kernel<false>, dim3(blocks), dim3(threads), args, 0, h->stream);
+        }
+        h->timing.launches += 1;
+    }
+    cudaEventRecord(h->ev[6], h->stream);
+    int written = 0;
+    if (e == cudaSuccess && rc == NBMF_OK) {
+        e = cudaMemcpyAsync(&written, nw, 4, cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess && keep) e = cudaMemcpyAsync(Z_samples, Zs, slice * nsamples, cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess && Z_last) e = cudaMemcpyAsync(Z_last, h->Z, slice, cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        float ms = 0; cudaEventElapsedTime(&ms, h->ev[0], h->ev[6]);
+        h->timing.total_ms = ms; h->timing.iters = iter > 1 ? iter - 1 : 0;
+    }
+    cudaFree(cF); cudaFree(cN); cudaFree(nw); cudaFree(Zs);
+    if (e != cudaSuccess) { h->err = std::string("collapsed Gibbs: ") + cudaGetErrorString(e); cudaGetLastError(); return NBMF_ERR_CUDA; }
+    if (rc) return rc;
+    if (n_samples_written) *n_samples_written = written;
+    // the statistics of the handle follow the labels (checkpoint / hand-off to VB)
+    return NBMF_OK;
+}
+
 extern "C" int nbmf_gibbs_sweep_given_W(nbmf_handle *h, const int32_t *v_n, const double *W, int64_t F,
                                         int K, double alpha, int iter, double burnin, uint64_t seed,
                                         double *C_mean)

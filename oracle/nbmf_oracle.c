@@ -680,6 +680,80 @@ int oracle_gibbs_dirber_finite(const int32_t *V, int32_t *Z, int F, int N, int K
 }
 
 /* ------------------------------------------------------------------------ */
+/* The same sweep with a counter-based uniform per entry instead of a        */
+/* sequential stream: u(f, n, i) = Philox4x32-10 keyed (seed; f, n, i)       */
+/* (Salmon et al. 2011).  Loop order, arithmetic and bookkeeping are those   */
+/* of Gibbs_DirBer_finite_Rcpp (collapsed_gibbs_z.cpp:392-427); only the     */
+/* source of the uniform differs, which makes the chain independent of the   */
+/* traversal order -- the engine's wavefront kernel must reproduce Z and     */
+/* Z_samples bit for bit.                                                    */
+/* ------------------------------------------------------------------------ */
+static void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1)
+{
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+    for (int r = 0; r < 10; r++) {
+        uint64_t p0 = (uint64_t)M0 * c[0], p1 = (uint64_t)M1 * c[2];
+        uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
+        uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+        uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+        k0 += W0; k1 += W1;
+    }
+}
+
+int oracle_gibbs_dirber_finite_keyed(const int32_t *V, int32_t *Z, int F, int N, int K, double alpha,
+                                     double beta, double gamma, int iter, double burnin, uint64_t seed,
+                                     int32_t *Z_samples)
+{
+    icounts cnt;
+    int nburnin = (int)floor(iter * burnin);
+    int nsamples = iter - (int)floor(iter * burnin);
+    int j = 0;
+    double *probs = malloc(sizeof(double) * K);
+    if (!probs || icounts_alloc(&cnt, F, K, N)) return -1;
+    if (Z_samples) memset(Z_samples, 0, 4 * (size_t)F * N * (nsamples > 0 ? nsamples : 0));
+    compute_counts(V, Z, &cnt); /* :388-389 */
+    for (int i = 1; i < iter; i++) { /* :392 */
+        for (int n = 0; n < N; n++)
+            for (int f = 0; f < F; f++) {
+                size_t e = (size_t)f + (size_t)F * n;
+                int v = V[e];
+                if (v == NA_INT) continue;
+                int k0 = Z[e]; /* remove_assignment :75-85 */
+                cnt.f_ones[n + (size_t)N * k0] -= v; cnt.f_zeros[n + (size_t)N * k0] -= 1 - v;
+                cnt.f_total[n + (size_t)N * k0] -= 1; cnt.n_total[f + (size_t)F * k0] -= 1;
+                cnt.fn_total[k0] -= 1;
+                double s = 0.0;
+                for (int k = 0; k < K; k++) { /* :402-407 */
+                    double gp = gamma + cnt.n_total[f + (size_t)F * k];
+                    double ap = alpha + cnt.f_ones[n + (size_t)N * k];
+                    double bp = beta + cnt.f_zeros[n + (size_t)N * k];
+                    probs[k] = gp * (v * ap + (1 - v) * bp) / (ap + bp);
+                    s += probs[k];
+                }
+                for (int k = 0; k < K; k++) probs[k] /= s; /* :408 */
+                uint32_t c[4] = {(uint32_t)f, (uint32_t)n, (uint32_t)i, 0u};
+                philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+                uint64_t bits = ((uint64_t)c[0] << 32) | c[1];
+                double u = ((double)(bits >> 11) + 0.5) * (1.0 / 9007199254740992.0), acc = 0.0;
+                int k1 = -1; /* :411-413 */
+                for (int k = 0; k < K && k1 < 0; k++) { acc += probs[k]; if (u < acc) k1 = k; }
+                if (k1 < 0) { k1 = K - 1; for (int k = K - 1; k >= 0; k--) if (probs[k] > 0.0) { k1 = k; break; } }
+                Z[e] = k1; /* set_assignment :63-72 */
+                cnt.f_ones[n + (size_t)N * k1] += v; cnt.f_zeros[n + (size_t)N * k1] += 1 - v;
+                cnt.f_total[n + (size_t)N * k1] += 1; cnt.n_total[f + (size_t)F * k1] += 1;
+                cnt.fn_total[k1] += 1;
+            }
+        if (i >= nburnin && Z_samples && j < nsamples) { /* :423-426 */
+            memcpy(Z_samples + (size_t)F * N * j, Z, 4 * (size_t)F * N);
+            j++;
+        }
+    }
+    free(probs); icounts_free(&cnt);
+    return j;
+}
+
+/* ------------------------------------------------------------------------ */
 /* expectation.GibbsDirBer  (R/generic_Gibbs_DirBer.R:54-101): per-sample    */
 /* E_W (Dirichlet mean) and E_H (Beta mean) from the counts of sample j,     */
 /* E_V = mean_j E_W E_H^T.  Also returns the across-sample means of E_W and  */
