@@ -701,9 +701,43 @@ static void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1)
     }
 }
 
-int oracle_gibbs_dirber_finite_keyed(const int32_t *V, int32_t *Z, int F, int N, int K, double alpha,
-                                     double beta, double gamma, int iter, double burnin, uint64_t seed,
-                                     int32_t *Z_samples)
+/* one entry of the sweep (:396-418) */
+static void gibbs_keyed_entry(const int32_t *V, int32_t *Z, icounts *cnt, double *probs, int F, int N, int K,
+                              double alpha, double beta, double gamma, uint64_t seed, int i, int f, int n)
+{
+    size_t e = (size_t)f + (size_t)F * n;
+    int v = V[e];
+    if (v == NA_INT) return;
+    int k0 = Z[e]; /* remove_assignment :75-85 */
+    cnt->f_ones[n + (size_t)N * k0] -= v; cnt->f_zeros[n + (size_t)N * k0] -= 1 - v;
+    cnt->f_total[n + (size_t)N * k0] -= 1; cnt->n_total[f + (size_t)F * k0] -= 1;
+    cnt->fn_total[k0] -= 1;
+    double s = 0.0;
+    for (int k = 0; k < K; k++) { /* :402-407 */
+        double gp = gamma + cnt->n_total[f + (size_t)F * k];
+        double ap = alpha + cnt->f_ones[n + (size_t)N * k];
+        double bp = beta + cnt->f_zeros[n + (size_t)N * k];
+        probs[k] = gp * (v * ap + (1 - v) * bp) / (ap + bp);
+        s += probs[k];
+    }
+    for (int k = 0; k < K; k++) probs[k] /= s; /* :408 */
+    uint32_t c[4] = {(uint32_t)f, (uint32_t)n, (uint32_t)i, 0u};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    uint64_t bits = ((uint64_t)c[0] << 32) | c[1];
+    double u = ((double)(bits >> 11) + 0.5) * (1.0 / 9007199254740992.0), acc = 0.0;
+    int k1 = -1; /* :411-413 */
+    for (int k = 0; k < K && k1 < 0; k++) { acc += probs[k]; if (u < acc) k1 = k; }
+    if (k1 < 0) { k1 = K - 1; for (int k = K - 1; k >= 0; k--) if (probs[k] > 0.0) { k1 = k; break; } }
+    Z[e] = k1; /* set_assignment :63-72 */
+    cnt->f_ones[n + (size_t)N * k1] += v; cnt->f_zeros[n + (size_t)N * k1] += 1 - v;
+    cnt->f_total[n + (size_t)N * k1] += 1; cnt->n_total[f + (size_t)F * k1] += 1;
+    cnt->fn_total[k1] += 1;
+}
+
+/* wavefront = 0: the reference's column-major order (:394-395); 1: anti-diagonals d = f + n
+ * (the engine's order; must give the same labels, tests/test_oracle.py)      */
+static int gibbs_keyed(const int32_t *V, int32_t *Z, int F, int N, int K, double alpha, double beta, double gamma,
+                       int iter, double burnin, uint64_t seed, int32_t *Z_samples, int wavefront)
 {
     icounts cnt;
     int nburnin = (int)floor(iter * burnin);
@@ -714,36 +748,16 @@ int oracle_gibbs_dirber_finite_keyed(const int32_t *V, int32_t *Z, int F, int N,
     if (Z_samples) memset(Z_samples, 0, 4 * (size_t)F * N * (nsamples > 0 ? nsamples : 0));
     compute_counts(V, Z, &cnt); /* :388-389 */
     for (int i = 1; i < iter; i++) { /* :392 */
-        for (int n = 0; n < N; n++)
-            for (int f = 0; f < F; f++) {
-                size_t e = (size_t)f + (size_t)F * n;
-                int v = V[e];
-                if (v == NA_INT) continue;
-                int k0 = Z[e]; /* remove_assignment :75-85 */
-                cnt.f_ones[n + (size_t)N * k0] -= v; cnt.f_zeros[n + (size_t)N * k0] -= 1 - v;
-                cnt.f_total[n + (size_t)N * k0] -= 1; cnt.n_total[f + (size_t)F * k0] -= 1;
-                cnt.fn_total[k0] -= 1;
-                double s = 0.0;
-                for (int k = 0; k < K; k++) { /* :402-407 */
-                    double gp = gamma + cnt.n_total[f + (size_t)F * k];
-                    double ap = alpha + cnt.f_ones[n + (size_t)N * k];
-                    double bp = beta + cnt.f_zeros[n + (size_t)N * k];
-                    probs[k] = gp * (v * ap + (1 - v) * bp) / (ap + bp);
-                    s += probs[k];
-                }
-                for (int k = 0; k < K; k++) probs[k] /= s; /* :408 */
-                uint32_t c[4] = {(uint32_t)f, (uint32_t)n, (uint32_t)i, 0u};
-                philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
-                uint64_t bits = ((uint64_t)c[0] << 32) | c[1];
-                double u = ((double)(bits >> 11) + 0.5) * (1.0 / 9007199254740992.0), acc = 0.0;
-                int k1 = -1; /* :411-413 */
-                for (int k = 0; k < K && k1 < 0; k++) { acc += probs[k]; if (u < acc) k1 = k; }
-                if (k1 < 0) { k1 = K - 1; for (int k = K - 1; k >= 0; k--) if (probs[k] > 0.0) { k1 = k; break; } }
-                Z[e] = k1; /* set_assignment :63-72 */
-                cnt.f_ones[n + (size_t)N * k1] += v; cnt.f_zeros[n + (size_t)N * k1] += 1 - v;
-                cnt.f_total[n + (size_t)N * k1] += 1; cnt.n_total[f + (size_t)F * k1] += 1;
-                cnt.fn_total[k1] += 1;
+        if (!wavefront) {
+            for (int n = 0; n < N; n++)
+                for (int f = 0; f < F; f++) gibbs_keyed_entry(V, Z, &cnt, probs, F, N, K, alpha, beta, gamma, seed, i, f, n);
+        } else {
+            for (int d = 0; d <= F + N - 2; d++) {
+                int f_lo = d - (N - 1) > 0 ? d - (N - 1) : 0, f_hi = d < F - 1 ? d : F - 1;
+                for (int f = f_hi; f >= f_lo; f--) /* any order within a diagonal */
+                    gibbs_keyed_entry(V, Z, &cnt, probs, F, N, K, alpha, beta, gamma, seed, i, f, d - f);
             }
+        }
         if (i >= nburnin && Z_samples && j < nsamples) { /* :423-426 */
             memcpy(Z_samples + (size_t)F * N * j, Z, 4 * (size_t)F * N);
             j++;
@@ -751,6 +765,20 @@ int oracle_gibbs_dirber_finite_keyed(const int32_t *V, int32_t *Z, int F, int N,
     }
     free(probs); icounts_free(&cnt);
     return j;
+}
+
+int oracle_gibbs_dirber_finite_keyed(const int32_t *V, int32_t *Z, int F, int N, int K, double alpha,
+                                     double beta, double gamma, int iter, double burnin, uint64_t seed,
+                                     int32_t *Z_samples)
+{
+    return gibbs_keyed(V, Z, F, N, K, alpha, beta, gamma, iter, burnin, seed, Z_samples, 0);
+}
+
+int oracle_gibbs_dirber_finite_keyed_wavefront(const int32_t *V, int32_t *Z, int F, int N, int K, double alpha,
+                                               double beta, double gamma, int iter, double burnin,
+                                               uint64_t seed, int32_t *Z_samples)
+{
+    return gibbs_keyed(V, Z, F, N, K, alpha, beta, gamma, iter, burnin, seed, Z_samples, 1);
 }
 
 /* ------------------------------------------------------------------------ */

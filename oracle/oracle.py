@@ -71,6 +71,8 @@ def lib():
                                                  C.c_uint64, _ip]
         L.oracle_gibbs_dirber_finite_keyed.restype = C.c_int
         L.oracle_gibbs_dirber_finite_keyed.argtypes = L.oracle_gibbs_dirber_finite.argtypes
+        L.oracle_gibbs_dirber_finite_keyed_wavefront.restype = C.c_int
+        L.oracle_gibbs_dirber_finite_keyed_wavefront.argtypes = L.oracle_gibbs_dirber_finite.argtypes
         L.oracle_gibbs_expectation.restype = C.c_int
         L.oracle_gibbs_expectation.argtypes = [_ip, _ip, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
                                                C.c_double, C.c_double, _dp, _dp, _dp]
@@ -192,13 +194,15 @@ def gibbs_dirber_finite(V, Z, K, alpha=1.0, beta=1.0, gamma=1.0, iter=100, burni
     return {"Z_samples": Zs[:, :, :ns], "written": j, "Z": Z}
 
 
-def gibbs_dirber_finite_keyed(V, Z, K, alpha=1.0, beta=1.0, gamma=1.0, iter=100, burnin=0.5, seed=1):
-    """The reference's collapsed sweep with the per-entry Philox key (seed; f, n, sweep) as its uniform."""
+def gibbs_dirber_finite_keyed(V, Z, K, alpha=1.0, beta=1.0, gamma=1.0, iter=100, burnin=0.5, seed=1, wavefront=False):
+    """The reference's collapsed sweep with the per-entry Philox key (seed; f, n, sweep) as its uniform;
+    `wavefront=True` visits the entries by anti-diagonals instead of column-major."""
     V = _i32(V); Z = _i32(Z).copy(order="F")
     F, N = V.shape
     ns = iter - int(np.floor(iter * burnin))
     Zs = np.zeros((F, N, max(ns, 1)), dtype=np.int32, order="F")
-    j = lib().oracle_gibbs_dirber_finite_keyed(_p(V, _ip), _p(Z, _ip), F, N, K, alpha, beta, gamma, iter, burnin,
+    fn = lib().oracle_gibbs_dirber_finite_keyed_wavefront if wavefront else lib().oracle_gibbs_dirber_finite_keyed
+    j = fn(_p(V, _ip), _p(Z, _ip), F, N, K, alpha, beta, gamma, iter, burnin,
                                                seed, _p(Zs, _ip))
     assert j >= 0
     return {"Z_samples": Zs[:, :, :ns], "written": j, "Z": Z}

@@ -144,6 +144,38 @@ def test_gibbs_bookkeeping_and_quirks():
     assert np.allclose(EW.sum(1), 1.0)
 
 
+@pytest.mark.parametrize("F,N,K,na", [(23, 31, 4, 0.2), (9, 40, 3, 0.0), (33, 8, 5, 0.4)])
+def test_keyed_collapsed_gibbs_is_order_independent(F, N, K, na):
+    """With the uniform of entry (f, n) in sweep i keyed by (seed; f, n, i), the reference's column-major
+    sweep and the anti-diagonal order visit every conflicting pair in the same order: same labels, same
+    Z_samples (this is what lets the GPU kernel be bit-exact)."""
+    V = make_problem(F, N, 3, 19, na)
+    Z = oracle.random_labels(V, K, 6)
+    a = oracle.gibbs_dirber_finite_keyed(V, Z, K, 1.0, 1.0, 0.5, iter=9, burnin=0.4, seed=12)
+    b = oracle.gibbs_dirber_finite_keyed(V, Z, K, 1.0, 1.0, 0.5, iter=9, burnin=0.4, seed=12, wavefront=True)
+    assert a["written"] == b["written"] == 6
+    assert np.array_equal(a["Z"], b["Z"]) and np.array_equal(a["Z_samples"], b["Z_samples"])
+    obs = V != NA
+    assert np.all((a["Z"][obs] >= 0) & (a["Z"][obs] < K))
+
+
+def test_keyed_and_stream_collapsed_gibbs_sample_the_same_posterior():
+    """The keyed uniforms replace the sequential stream, nothing else: the posterior mean of V (label
+    invariant) of the two chains agrees within the seed-to-seed spread of either."""
+    F, N, K = 20, 30, 3
+    V = make_problem(F, N, 3, 23)
+    ev_s, ev_k = [], []
+    for seed in (1, 2, 3):
+        Z = oracle.random_labels(V, K, seed)
+        a = oracle.gibbs_dirber_finite(V, Z, K, iter=300, burnin=0.5, seed=seed)
+        ev_s.append(oracle.gibbs_expectation(V, a["Z_samples"][:, :, :a["written"]], K, 1.0, 1.0, 1.0)[2])
+        b = oracle.gibbs_dirber_finite_keyed(V, Z, K, iter=300, burnin=0.5, seed=seed)
+        ev_k.append(oracle.gibbs_expectation(V, b["Z_samples"][:, :, :b["written"]], K, 1.0, 1.0, 1.0)[2])
+    rms_between = np.sqrt(np.mean((np.mean(ev_s, 0) - np.mean(ev_k, 0)) ** 2))
+    rms_within = np.sqrt(np.mean((ev_s[0] - ev_s[1]) ** 2))
+    assert rms_between < 2.0 * max(rms_within, 0.01)
+
+
 def test_collapsed_vs_uncollapsed_gibbs_agree():
     """Different chains, same posterior: predictive LL per held-out entry and E_V
     agree within the seed-to-seed spread (SURVEY.md Appendix E probe 4)."""
