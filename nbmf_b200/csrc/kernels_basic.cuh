@@ -491,49 +491,71 @@ struct WaveArgs {
     double *bvb;    // [N][Kc]
 };
 
-template <bool SINGLE_BLOCK>
+// G lanes (a power of two <= 32) share one entry and split k; everything that the reference does
+// independently per k (counter updates, the divisions) runs in parallel, and only the two
+// order-sensitive reductions stay sequential: the running sum over k is carried through the
+// group with shuffles in the reference's order k = 0, 1, ..., so the result is bit-identical to
+// the one-thread-per-entry form while the critical path per entry drops from 2 Kc divisions to
+// two divisions and Kc additions.
+template <bool SINGLE_BLOCK, int G>
 __global__ void __launch_bounds__(1024) cvb0_wavefront_kernel(WaveArgs a)
 {
     cg::grid_group grid = cg::this_grid();
     const int64_t F = a.F, N = a.N;
     const int Kc = a.Kc;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    const int64_t ngroups = ((int64_t)gridDim.x * blockDim.x) / G;
+    const int64_t gid = tid / G;
+    const int gl = (int)(tid & (G - 1));                 // lane within the group
+    const int gbase = (threadIdx.x & 31) & ~(G - 1);     // first warp lane of the group
     for (int sweep = 0; sweep < a.sweeps; sweep++) {
         for (int64_t d = 0; d <= F + N - 2; d++) {
             const int64_t f_lo = d - (N - 1) > 0 ? d - (N - 1) : 0;
             const int64_t f_hi = d < F - 1 ? d : F - 1;
-            for (int64_t f = f_lo + tid; f <= f_hi; f += nthreads) {
+            const int64_t cnt = f_hi - f_lo + 1;
+            // uniform trip count: the shuffles below need every lane of the warp
+            for (int64_t base = 0; base < cnt; base += ngroups) {
+                const int64_t f = f_lo + base + gid;
                 const int64_t n = d - f;
-                const uint32_t mw = a.mc ? a.mc[n * a.Fw + (f >> 5)] : 0xffffffffu;
-                if (!((mw >> (f & 31)) & 1u)) continue;
-                const int v = (a.vc[n * a.Fw + (f >> 5)] >> (f & 31)) & 1u;
-                double *ez = a.EZ + (n * F + f) * Kc;
-                double *nt = a.cF + f * Kc, *fo = a.cN1 + n * Kc, *fz = a.cN0 + n * Kc;
-                double *gv = a.gvb + f * Kc, *av = a.avb + n * Kc, *bv = a.bvb + n * Kc;
-                double s = 0.0;
-                for (int k = 0; k < Kc; k++) {
-                    const double p = ez[k];
-                    // remove_vbassignment (:81-92)
-                    const double o1 = __dsub_rn(fo[k], v ? p : 0.0);
-                    const double o0 = __dsub_rn(fz[k], v ? 0.0 : p);
-                    const double t = __dsub_rn(nt[k], p);
-                    fo[k] = o1; fz[k] = o0; nt[k] = t;
-                    // :128-133
-                    const double g = __dadd_rn(a.gamma, t);
-                    const double al = __dadd_rn(a.alpha, o1);
-                    const double be = __dadd_rn(a.beta, o0);
-                    gv[k] = g; av[k] = al; bv[k] = be;
-                    const double pr = __ddiv_rn(__dmul_rn(g, v ? al : be), __dadd_rn(al, be));
-                    ez[k] = pr;
-                    s = __dadd_rn(s, pr);
+                bool act = (base + gid) < cnt;
+                int v = 0;
+                if (act) {
+                    const uint32_t mw = a.mc ? a.mc[n * a.Fw + (f >> 5)] : 0xffffffffu;
+                    act = (mw >> (f & 31)) & 1u;
+                    v = (a.vc[n * a.Fw + (f >> 5)] >> (f & 31)) & 1u;
                 }
-                for (int k = 0; k < Kc; k++) {
-                    const double pr = __ddiv_rn(ez[k], s); // :134
-                    ez[k] = pr;                            // set_vbassignment (:69-78)
-                    fo[k] = __dadd_rn(fo[k], v ? pr : 0.0);
-                    fz[k] = __dadd_rn(fz[k], v ? 0.0 : pr);
-                    nt[k] = __dadd_rn(nt[k], pr);
+                const int64_t fs = act ? f : 0, ns = act ? n : 0;    // inactive groups compute on row 0, store nothing
+                double *ez = a.EZ + (ns * F + fs) * Kc;
+                double *nt = a.cF + fs * Kc, *fo = a.cN1 + ns * Kc, *fz = a.cN0 + ns * Kc;
+                double *gv = a.gvb + fs * Kc, *av = a.avb + ns * Kc, *bv = a.bvb + ns * Kc;
+                double s = 0.0;
+                for (int k0 = 0; k0 < Kc; k0 += G) {
+                    const int k = k0 + gl;
+                    double pr = 0.0;
+                    if (k < Kc) {
+                        const double p = ez[k];
+                        // remove_vbassignment (:81-92)
+                        const double o1 = __dsub_rn(fo[k], v ? p : 0.0);
+                        const double o0 = __dsub_rn(fz[k], v ? 0.0 : p);
+                        const double t = __dsub_rn(nt[k], p);
+                        // :128-133
+                        const double g = __dadd_rn(a.gamma, t);
+                        const double al = __dadd_rn(a.alpha, o1);
+                        const double be = __dadd_rn(a.beta, o0);
+                        pr = __ddiv_rn(__dmul_rn(g, v ? al : be), __dadd_rn(al, be));
+                        if (act) { fo[k] = o1; fz[k] = o0; nt[k] = t; gv[k] = g; av[k] = al; bv[k] = be; ez[k] = pr; }
+                    }
+                    const int kn = Kc - k0 < G ? Kc - k0 : G;
+                    for (int j = 0; j < kn; j++) s = __dadd_rn(s, __shfl_sync(0xffffffffu, pr, gbase + j));
+                }
+                if (act) {
+                    for (int k = gl; k < Kc; k += G) {
+                        const double pr = __ddiv_rn(ez[k], s); // :134
+                        ez[k] = pr;                            // set_vbassignment (:69-78)
+                        fo[k] = __dadd_rn(fo[k], v ? pr : 0.0);
+                        fz[k] = __dadd_rn(fz[k], v ? 0.0 : pr);
+                        nt[k] = __dadd_rn(nt[k], pr);
+                    }
                 }
             }
             if (SINGLE_BLOCK) __syncthreads();
@@ -565,7 +587,7 @@ struct GibbsWaveArgs {
     int *n_written;
 };
 
-template <bool SINGLE_BLOCK>
+template <bool SINGLE_BLOCK, int G>
 __global__ void __launch_bounds__(1024) gibbs_collapsed_wavefront_kernel(GibbsWaveArgs a)
 {
     cg::grid_group grid = cg::this_grid();
@@ -573,56 +595,80 @@ __global__ void __launch_bounds__(1024) gibbs_collapsed_wavefront_kernel(GibbsWa
     const int K = a.K;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
-    int j = 0;
+    const int64_t ngroups = nthreads / G;
+    const int64_t gid = tid / G;
+    const int gl = (int)(tid & (G - 1));
+    const int gbase = (threadIdx.x & 31) & ~(G - 1);
+    int jw = 0;
     for (int i = 1; i < a.iter; i++) {   // :392
         for (int64_t d = 0; d <= F + N - 2; d++) {
             const int64_t f_lo = d - (N - 1) > 0 ? d - (N - 1) : 0;
             const int64_t f_hi = d < F - 1 ? d : F - 1;
-            for (int64_t f = f_lo + tid; f <= f_hi; f += nthreads) {
+            const int64_t cnt = f_hi - f_lo + 1;
+            for (int64_t base = 0; base < cnt; base += ngroups) {   // uniform trip count (shuffles)
+                const int64_t f = f_lo + base + gid;
                 const int64_t n = d - f;
-                const uint32_t mw = a.mc ? a.mc[n * a.Fw + (f >> 5)] : 0xffffffffu;
-                if (!((mw >> (f & 31)) & 1u)) continue;
-                const int v = (a.vc[n * a.Fw + (f >> 5)] >> (f & 31)) & 1u;
-                int32_t *nF = a.cF + f * K, *nV = a.cN + (2 * n + v) * K;
-                const int32_t *n1 = a.cN + (2 * n + 1) * K, *n0 = a.cN + (2 * n) * K;
-                const int k0 = a.Z[f + F * n];
-                nF[k0] -= 1; nV[k0] -= 1;   // remove_assignment (:75-85)
-                double s = 0.0;
-                for (int k = 0; k < K; k++) {   // :402-407
-                    const double gp = __dadd_rn(a.gamma, (double)nF[k]);
-                    const double ap = __dadd_rn(a.alpha, (double)n1[k]);
-                    const double bp = __dadd_rn(a.beta, (double)n0[k]);
-                    s = __dadd_rn(s, __ddiv_rn(__dmul_rn(gp, v ? ap : bp), __dadd_rn(ap, bp)));
+                bool act = (base + gid) < cnt;
+                int v = 0;
+                if (act) {
+                    const uint32_t mw = a.mc ? a.mc[n * a.Fw + (f >> 5)] : 0xffffffffu;
+                    act = (mw >> (f & 31)) & 1u;
+                    v = (a.vc[n * a.Fw + (f >> 5)] >> (f & 31)) & 1u;
                 }
-                const philox4 r = philox4x32_10((uint32_t)f, (uint32_t)n, (uint32_t)i, 0u, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+                const int64_t fs = act ? f : 0, ns = act ? n : 0;
+                int32_t *nF = a.cF + fs * K, *nV = a.cN + (2 * ns + v) * K;
+                const int32_t *n1 = a.cN + (2 * ns + 1) * K, *n0 = a.cN + (2 * ns) * K;
+                const int k_old = act ? a.Z[fs + F * ns] : -1;
+                // probabilities with the entry's own assignment removed (:396-407); the counts in
+                // memory are only touched once, at the end, by the group's first lane
+                auto prob = [&](int k) {
+                    const int own = (k == k_old) ? 1 : 0;
+                    const double gp = __dadd_rn(a.gamma, (double)(nF[k] - own));
+                    const double ap = __dadd_rn(a.alpha, (double)(n1[k] - (v ? own : 0)));
+                    const double bp = __dadd_rn(a.beta, (double)(n0[k] - (v ? 0 : own)));
+                    return __ddiv_rn(__dmul_rn(gp, v ? ap : bp), __dadd_rn(ap, bp));
+                };
+                double s = 0.0;
+                for (int k0 = 0; k0 < K; k0 += G) {
+                    const int k = k0 + gl;
+                    const double q = k < K ? prob(k) : 0.0;
+                    const int kn = K - k0 < G ? K - k0 : G;
+                    for (int j = 0; j < kn; j++) s = __dadd_rn(s, __shfl_sync(0xffffffffu, q, gbase + j));
+                }
+                const philox4 r = philox4x32_10((uint32_t)fs, (uint32_t)ns, (uint32_t)i, 0u, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
                 const double u = u64_to_unif(r.x, r.y);
                 double c = 0.0;
                 int k1 = -1, last_pos = K - 1;
-                for (int k = 0; k < K; k++) {   // :408, inverse CDF in place of rmultinom + index_max (:411-413)
-                    const double gp = __dadd_rn(a.gamma, (double)nF[k]);
-                    const double ap = __dadd_rn(a.alpha, (double)n1[k]);
-                    const double bp = __dadd_rn(a.beta, (double)n0[k]);
-                    const double pr = __ddiv_rn(__ddiv_rn(__dmul_rn(gp, v ? ap : bp), __dadd_rn(ap, bp)), s);
-                    c = __dadd_rn(c, pr);
-                    if (pr > 0.0) last_pos = k;
-                    if (k1 < 0 && u < c) k1 = k;
+                for (int k0 = 0; k0 < K; k0 += G) {   // :408, inverse CDF in place of rmultinom + index_max (:411-413)
+                    const int k = k0 + gl;
+                    const double pr = k < K ? __ddiv_rn(prob(k), s) : 0.0;
+                    const int kn = K - k0 < G ? K - k0 : G;
+                    for (int j = 0; j < kn; j++) {
+                        const double pj = __shfl_sync(0xffffffffu, pr, gbase + j);
+                        c = __dadd_rn(c, pj);
+                        if (pj > 0.0) last_pos = k0 + j;
+                        if (k1 < 0 && u < c) k1 = k0 + j;
+                    }
                 }
                 if (k1 < 0) k1 = last_pos;
-                a.Z[f + F * n] = k1;        // set_assignment (:63-72)
-                nF[k1] += 1; nV[k1] += 1;
+                if (act && gl == 0) {
+                    nF[k_old] -= 1; nV[k_old] -= 1;   // remove_assignment (:75-85)
+                    a.Z[fs + F * ns] = k1;            // set_assignment (:63-72)
+                    nF[k1] += 1; nV[k1] += 1;
+                }
             }
             if (SINGLE_BLOCK) __syncthreads();
             else grid.sync();
         }
-        if (i >= a.nburnin && a.Z_samples && j < a.nsamples) {   // :423-426
-            int32_t *dst = a.Z_samples + (int64_t)j * F * N;
+        if (i >= a.nburnin && a.Z_samples && jw < a.nsamples) {   // :423-426
+            int32_t *dst = a.Z_samples + (int64_t)jw * F * N;
             for (int64_t e = tid; e < F * N; e += nthreads) dst[e] = a.Z[e];
-            j++;
+            jw++;
             if (SINGLE_BLOCK) __syncthreads();
             else grid.sync();
-        } else if (i >= a.nburnin && j < a.nsamples) j++;
+        } else if (i >= a.nburnin && jw < a.nsamples) jw++;
     }
-    if (tid == 0) *a.n_written = j;
+    if (tid == 0) *a.n_written = jw;
 }
 
 // one-hot E_Z [n][f][Kc] + counters from labels (commons.cpp:29-42,

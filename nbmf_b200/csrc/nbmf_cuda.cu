@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <type_traits>
 #include <vector>
 
 #define CK(call) NBMF_CUDA_CHECK(h, call)
@@ -825,6 +826,49 @@ extern "C" int nbmf_lower_bound(nbmf_handle *h, int K, double alpha, double beta
 // ---------------------------------------------------------------------------
 // VB_DirBer_Rcpp
 // ---------------------------------------------------------------------------
+// Launch a wavefront kernel with G lanes per entry (G = smallest power of two >= Kc in [4, 32], halved
+// while that lets a diagonal fit one 1024-thread pass): one block
+// while a diagonal needs at most four passes of 1024 threads (block barrier), else a cooperative
+// grid (grid barrier between diagonals).
+template <template <bool, int> class KERN, typename ARGS>
+static cudaError_t launch_wavefront(nbmf_handle *h, ARGS &a, int Kc, int64_t diag)
+{
+    int G = 4;
+    while (G < Kc && G < 32) G <<= 1;
+    // a short diagonal is better served by one pass of one block than by more lanes per entry
+    while (G > 4 && diag * G > 1024 && diag * (G / 2) <= 1024) G >>= 1;
+    const int64_t need = diag * G;
+    const bool single = need <= 4096;
+    const int threads = single ? (int)std::min<int64_t>(1024, std::max<int64_t>(32, round_up64(need, 32))) : 256;
+    void *args[] = {&a};
+    auto go = [&](auto gtag) -> cudaError_t {
+        constexpr int GG = decltype(gtag)::value;
+        if (single) {
+            KERN<true, GG>::launch(a, 1, threads, h->stream);
+            return cudaGetLastError();
+        }
+        int per_sm = 0;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, KERN<false, GG>::ptr(), threads, 0);
+        if (e != cudaSuccess) return e;
+        const int blocks = (int)std::min<int64_t>((need + threads - 1) / threads, (int64_t)per_sm * h->sm_count);
+        return cudaLaunchCooperativeKernel(KERN<false, GG>::ptr(), dim3(blocks), dim3(threads), args, 0, h->stream);
+    };
+    switch (G) {
+    case 4: return go(std::integral_constant<int, 4>{});
+    case 8: return go(std::integral_constant<int, 8>{});
+    case 16: return go(std::integral_constant<int, 16>{});
+    default: return go(std::integral_constant<int, 32>{});
+    }
+}
+template <bool SB, int G> struct Cvb0Kern {
+    static void *ptr() { return (void *)cvb0_wavefront_kernel<SB, G>; }
+    static void launch(WaveArgs &a, int blocks, int threads, cudaStream_t st) { cvb0_wavefront_kernel<SB, G><<<blocks, threads, 0, st>>>(a); }
+};
+template <bool SB, int G> struct GibbsWaveKern {
+    static void *ptr() { return (void *)gibbs_collapsed_wavefront_kernel<SB, G>; }
+    static void launch(GibbsWaveArgs &a, int blocks, int threads, cudaStream_t st) { gibbs_collapsed_wavefront_kernel<SB, G><<<blocks, threads, 0, st>>>(a); }
+};
+
 static int dirber_wavefront(nbmf_handle *h, int K, double alpha, double beta, double gamma, int iter,
                             double *E_W, double *E_H, double *E_Z)
 {
@@ -856,19 +900,7 @@ static int dirber_wavefront(nbmf_handle *h, int K, double alpha, double beta, do
         e = cudaGetLastError();
     }
     if (e == cudaSuccess && a.sweeps > 0) {
-        int64_t diag = std::min(F, N);
-        if (diag <= 1024) {
-            int threads = (int)std::max<int64_t>(32, round_up64(diag, 32));
-            cvb0_wavefront_kernel<true><<<1, threads, 0, h->stream>>>(a);
-            e = cudaGetLastError();
-        } else {
-            int threads = 256, per_sm = 0;
-            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cvb0_wavefront_kernel<false>, threads, 0);
-            int blocks = (int)std::min<int64_t>((diag + threads - 1) / threads, (int64_t)per_sm * h->sm_count);
-            void *args[] = {&a};
-            if (e == cudaSuccess)
-                e = cudaLaunchCooperativeKernel((void *)cvb0_wavefront_kernel<false>, dim3(blocks), dim3(threads), args, 0, h->stream);
-        }
+        e = launch_wavefront<Cvb0Kern>(h, a, Kc, std::min(F, N));
         h->timing.launches += 1;
     }
     double *outW = nullptr;
@@ -1102,19 +1134,7 @@ extern "C" int nbmf_gibbs_dirber_collapsed(nbmf_handle *h, int K, double alpha, 
         a.K = K; a.iter = iter; a.nburnin = nburnin; a.nsamples = nsamples;
         a.alpha = alpha; a.beta = beta; a.gamma = gamma; a.seed = seed;
         a.Z = h->Z; a.cF = cF; a.cN = cN; a.Z_samples = keep ? Zs : nullptr; a.n_written = nw;
-        const int64_t diag = std::min(F, N);
-        if (diag <= 1024) {
-            int threads = (int)std::max<int64_t>(32, round_up64(diag, 32));
-            gibbs_collapsed_wavefront_kernel<true><<<1, threads, 0, h->stream>>>(a);
-            e = cudaGetLastError();
-        } else {
-            int threads = 256, per_sm = 0;
-            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gibbs_collapsed_wavefront_kernel<false>, threads, 0);
-            int blocks = (int)std::min<int64_t>((diag + threads - 1) / threads, (int64_t)per_sm * h->sm_count);
-            void *args[] = {&a};
-            if (e == cudaSuccess)
-                e = cudaLaunchCooperativeKernel((void *)gibbs_collapsed_wavefront_kernel<false>, dim3(blocks), dim3(threads), args, 0, h->stream);
-        }
+        e = launch_wavefront<GibbsWaveKern>(h, a, K, std::min(F, N));
         h->timing.launches += 1;
     }
     cudaEventRecord(h->ev[6], h->stream);
