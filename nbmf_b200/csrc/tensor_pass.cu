@@ -799,21 +799,23 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
             float log_acc = 0.f;
             const int64_t orow = ROWS ? l : (l >> 1);
             const uint32_t bsel = ROWS ? 0u : (uint32_t)(l & 1);
-            const uint32_t *vrow = a.vbits + orow * a.words;
-            const uint32_t *mrow = a.mbits + orow * a.words;
-            // bits per step: ROWS: 32 n -> 1 word; COLS: 64 f -> 2 words
+            // bits per step: ROWS: 32 n -> 1 word; COLS: 64 f -> 2 words.  Running pointers (one step of
+            // this group = 4 steps of the item) instead of an index product per step.
             constexpr int WPS = ROWS ? 1 : 2;
+            const int tfirst = (int)(((uint32_t)grp - base) & 3u);
+            const uint32_t *vp = a.vbits + orow * a.words + (t0 + tfirst) * WPS;
+            const uint32_t *mp = a.mbits + orow * a.words + (t0 + tfirst) * WPS;
             uint32_t bv[WPS], bm[WPS];
-            auto load_bits = [&](int t) {
-                const int64_t wi = (t0 + t) * WPS;
+            auto load_bits = [&]() {
 #pragma unroll
                 for (int i = 0; i < WPS; i++) {
-                    bv[i] = lane_ok ? __ldg(vrow + wi + i) : 0u;
-                    bm[i] = HAS_NA ? (lane_ok ? __ldg(mrow + wi + i) : 0u) : 0xffffffffu;
+                    bv[i] = lane_ok ? __ldg(vp + i) : 0u;
+                    bm[i] = HAS_NA ? (lane_ok ? __ldg(mp + i) : 0u) : 0xffffffffu;
                 }
+                vp += 4 * WPS;
+                if (HAS_NA) mp += 4 * WPS;
             };
-            const int tfirst = (int)(((uint32_t)grp - base) & 3u);
-            if (tfirst < nst) load_bits(tfirst);
+            if (tfirst < nst) load_bits();
             PROF_ACC(0);
             for (int t = tfirst; t < nst && ok; t += 4) {
                 uint32_t sel[WPS], vv[WPS];
@@ -822,7 +824,7 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
                     vv[i] = bv[i];
                     sel[i] = ROWS ? bm[i] : ((bsel ? bv[i] : ~bv[i]) & bm[i]);
                 }
-                if (t + 4 < nst) load_bits(t + 4);
+                if (t + 4 < nst) load_bits();
                 const uint32_t gs = base + (uint32_t)t;
                 const uint32_t s_use = gs / 3u, sslot = gs - 3u * s_use;
                 const uint32_t t_s = tmem + lane_addr + C::COL_S + 64 * sslot;
