@@ -31,6 +31,8 @@ __global__ void hop_kernel(int mode, int iters, long long *out)
     __shared__ uint32_t tmem_base;
     const uint32_t b0 = smem_u32(&bars[0]), b1 = smem_u32(&bars[1]);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool spin = mode >= 10;
+    if (spin) mode -= 10;
     if (threadIdx.x == 0) {
         mbar_init(b0, 1);
         mbar_init(b1, mode == 2 ? 128 : 1);
@@ -41,8 +43,6 @@ __global__ void hop_kernel(int mode, int iters, long long *out)
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     __syncthreads();
-    const bool spin = mode >= 10;
-    if (spin) mode -= 10;
     long long t0 = clock64();
     if (mode == 3) {
         if (threadIdx.x == 0) {
