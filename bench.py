@@ -164,7 +164,7 @@ def main():
     import torch
     import torch.distributed as dist
     from nbmf_b200 import Engine
-    from nbmf_b200.dist import make_allreduce_hook, shard_columns
+    from nbmf_b200.dist import init_nccl, make_allreduce_hook, shard_columns
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -174,7 +174,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        init_nccl(dev)
     F, N, K = wl["F"], wl["N"], wl["K"]
     n_lo, n_hi = shard_columns(N, rank, world)
     Nl = n_hi - n_lo

@@ -57,6 +57,10 @@ struct nbmf_handle {
     nbmf_allreduce_fn hook = nullptr; void *hook_ctx = nullptr;
     nbmf_timing timing{};
     cudaEvent_t ev[8] = {};
+    // exchange overlapped with the cols pass: side stream + begin / end events
+    cudaStream_t xchg_stream = nullptr;
+    cudaEvent_t xchg_ev[2] = {};
+    bool xchg_pending = false;
     // pipelined upload (nbmf_vb_aspect_bits): copy stream, one event per column block
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t pipe_ev[33] = {};

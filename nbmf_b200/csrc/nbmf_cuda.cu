@@ -106,6 +106,7 @@ extern "C" void nbmf_destroy(nbmf_handle *h)
     for (int i = 0; i < 8; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     for (int i = 0; i < 33; i++) if (h->pipe_ev[i]) cudaEventDestroy(h->pipe_ev[i]);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->xchg_stream) { cudaStreamDestroy(h->xchg_stream); cudaEventDestroy(h->xchg_ev[0]); cudaEventDestroy(h->xchg_ev[1]); }
     cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -163,6 +164,38 @@ static int exchange(nbmf_handle *h, double *buf, size_t count)
 // ---------------------------------------------------------------------------
 // data
 // ---------------------------------------------------------------------------
+// The same exchange started on a side stream behind the current point of the main stream, so
+// that whatever the main stream launches next overlaps it; exchange_end makes the main stream
+// wait for the result.  The side stream has the highest priority: the collective's few CTAs are
+// placed before the persistent contraction kernel that follows, whose work queue absorbs the
+// SMs that come late.
+static int exchange_begin(nbmf_handle *h, double *buf, size_t count)
+{
+    if (!h->hook) return NBMF_OK;
+    if (!h->xchg_stream) {
+        int lo = 0, hi = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CK(cudaStreamCreateWithPriority(&h->xchg_stream, cudaStreamNonBlocking, hi));
+        CK(cudaEventCreateWithFlags(&h->xchg_ev[0], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->xchg_ev[1], cudaEventDisableTiming));
+    }
+    CK(cudaEventRecord(h->xchg_ev[0], h->stream));
+    CK(cudaStreamWaitEvent(h->xchg_stream, h->xchg_ev[0], 0));
+    int rc = h->hook(h->hook_ctx, buf, count, (void *)h->xchg_stream);
+    if (rc != 0) return fail(h, NBMF_ERR_CUDA, "all-reduce hook failed");
+    CK(cudaEventRecord(h->xchg_ev[1], h->xchg_stream));
+    h->xchg_pending = true;
+    h->timing.launches += 1;
+    return NBMF_OK;
+}
+static int exchange_end(nbmf_handle *h)
+{
+    if (!h->xchg_pending) return NBMF_OK;
+    h->xchg_pending = false;
+    CK(cudaStreamWaitEvent(h->stream, h->xchg_ev[1], 0));
+    return NBMF_OK;
+}
+
 static int alloc_planes(nbmf_handle *h, int64_t F, int64_t N)
 {
     CK(cudaSetDevice(h->device));
@@ -623,11 +656,16 @@ extern "C" int nbmf_vb_step(nbmf_handle *h, int checklb)
     if ((rc = run_pass(h, 1, checklb ? h->scal + SC_SUMLOGD : nullptr))) return rc;
     if (checklb && use_tensor_path(h) && (rc = tp_log_correction(h, 1, h->scal + SC_SUMLOGD))) return rc;
     CK(cudaEventRecord(h->ev[3], h->stream));
-    if ((rc = exchange(h, h->GF, (size_t)h->F * h->Kp))) return rc;
+    // the cols pass needs nothing from the exchange (both statistics follow from the parameters),
+    // so on the tensor path the exchange runs beside it and is joined before the finalisation
+    if (use_tensor_path(h)) rc = exchange_begin(h, h->GF, (size_t)h->F * h->Kp);
+    else rc = exchange(h, h->GF, (size_t)h->F * h->Kp);
+    if (rc) return rc;
     CK(cudaEventRecord(h->ev[4], h->stream));
     // Beta-side statistics: owner = (column, branch) lanes, all local
     if ((rc = run_pass(h, 0, nullptr))) return rc;
     if (checklb && use_tensor_path(h) && (rc = tp_log_correction(h, 0, h->scal + SC_SUMLOGD))) return rc;
+    if ((rc = exchange_end(h))) return rc;
     }
     if (use_tensor_path(h)) {
         if ((rc = tp_finalize(h))) return rc;

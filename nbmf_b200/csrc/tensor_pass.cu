@@ -46,6 +46,7 @@ struct TPState {
     __half *A_hi = nullptr, *A_lo = nullptr;   // [Fpad][KP]
     __half *B_hi = nullptr, *B_lo = nullptr;   // [N2pad][KP]
     float *partial = nullptr; size_t partial_bytes = 0;
+    int *item_ctr = nullptr;              // work-queue counter of the running launch
     float *partial2 = nullptr; size_t partial2_bytes = 0;   // cols-pass partials of the pipelined step
     CUtensorMap tmA, tmB, tmAlo, tmBlo;
     unsigned long long *dmax = nullptr;   // [0] max A bits, [1] max BB bits
@@ -93,7 +94,7 @@ void tp_free(nbmf_handle *h)
     TPState *s = (TPState *)h->tp;
     if (!s) return;
     cudaFree(s->A_hi); cudaFree(s->A_lo); cudaFree(s->B_hi); cudaFree(s->B_lo);
-    cudaFree(s->partial); cudaFree(s->partial2); cudaFree(s->dmax); cudaFree(s->dexp); cudaFree(s->dacc); cudaFree(s->derr);
+    cudaFree(s->partial); cudaFree(s->partial2); cudaFree(s->dmax); cudaFree(s->dexp); cudaFree(s->dacc); cudaFree(s->derr); cudaFree(s->item_ctr);
     cudaFree(s->cntF); cudaFree(s->cntN);
     delete s;
     h->tp = nullptr;
@@ -138,6 +139,7 @@ int tp_prepare(nbmf_handle *h)
     if (e == cudaSuccess) e = cudaMalloc(&s->dexp, 8);
     if (e == cudaSuccess) e = cudaMalloc(&s->dacc, 16);
     if (e == cudaSuccess) e = cudaMalloc(&s->derr, 16);
+    if (e == cudaSuccess) e = cudaMalloc(&s->item_ctr, 16);
     if (e == cudaSuccess) e = cudaMalloc(&s->cntF, (size_t)h->F * 8);
     if (e == cudaSuccess) e = cudaMalloc(&s->cntN, (size_t)2 * h->N * 8);
     if (e != cudaSuccess) { cudaGetLastError(); tp_free(h); h->err = "tensor path allocation failed"; return NBMF_ERR_OOM; }
@@ -495,6 +497,7 @@ struct TPArgs {
     int64_t owner_tiles, tile_begin, owner_tiles_total;
     int64_t step_begin, step_end;  // steps of 64 streamed rows
     int chunk_steps, n_chunks, chunk_base;
+    int *item_ctr;                 // work queue: next item of this launch (zeroed by the host)
     float *partial;                // [chunks of all launches][owner_tiles_total*128][KP]
     const int *dexp;               // eA, eB
     double *dacc;                  // [0] += sum log2 S over selected entries (rows pass only)
@@ -534,7 +537,7 @@ struct TPCfg {
     static constexpr int COL_R = KP + 64 * NS;              // + 32 * (step % NR)
     static constexpr int COL_U = COL_R + 32 * NR;           // KP/2 columns; KP = 128: 448 + 64 = 512
     static constexpr int SMEM_BYTES = STAGES * TILE_BYTES + 1024 /*align*/ + 512 /*barriers*/;
-    static_assert(2 * STAGES + NS + 3 * NR + 2 <= 64, "barrier area");
+    static_assert(2 * STAGES + NS + 3 * NR + 2 + 8 <= 64, "barrier area");
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory");
 };
 
@@ -557,8 +560,14 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
     const uint32_t BAR_RFREE = BAR_RREADY + 8u * C::NR;               // [NR] stage 2 done           (commit)
     const uint32_t BAR_GFULL = BAR_RFREE + 8u * C::NR;
     const uint32_t BAR_UREADY = BAR_GFULL + 8;
+    // Work items come from a global counter (one atomicAdd per item by the producer thread) and
+    // reach the other roles through a 4-entry ring: CTAs that start late -- e.g. because the
+    // exchange's NCCL kernel holds their SM for the first millisecond -- simply take fewer items.
+    const uint32_t BAR_IFULL = BAR_UREADY + 8;                        // [4] item published          (1 arrival)
+    const uint32_t BAR_IEMPTY = BAR_IFULL + 8u * 4;                   // [4] item read by every role (2 + 512 arrivals)
     __shared__ uint32_t tmem_base_sh;
     __shared__ int abort_sh;
+    __shared__ int item_ring[4];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     volatile int *abort_flag = &abort_sh;
@@ -570,6 +579,7 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
         for (int s = 0; s < C::NR; s++) { mbar_init(BAR_SFULL + 8u * s, 1); mbar_init(BAR_RREADY + 8u * s, 128); mbar_init(BAR_RFREE + 8u * s, 1); }
         mbar_init(BAR_GFULL, 1);
         mbar_init(BAR_UREADY, 512);
+        for (int s = 0; s < 4; s++) { mbar_init(BAR_IFULL + 8u * s, 1); mbar_init(BAR_IEMPTY + 8u * s, 2 + 512); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -582,6 +592,15 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
     const uint32_t tmem = tmem_base_sh;
 
     const int64_t n_items = (int64_t)a.n_chunks * a.owner_tiles;
+    // next item for a consumer role (it = how many items the role has taken so far); -1 = stop
+    auto take_item = [&](uint32_t &it, int code) -> int64_t {
+        const uint32_t is = it & 3u, ip = (it >> 2) & 1u;
+        if (!mbar_wait(BAR_IFULL + 8u * is, ip, abort_flag, code)) return -1;
+        const int w = *(volatile int *)&item_ring[is];
+        mbar_arrive(BAR_IEMPTY + 8u * is);
+        it++;
+        return w < n_items ? (int64_t)w : -1;
+    };
     const int eU = ROWS ? a.dexp[0] : a.dexp[1];
     const int eW = ROWS ? a.dexp[1] : a.dexp[0];
 
@@ -590,7 +609,13 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
         if (elect_one()) {
             uint32_t stage = 0, phase = 0;
             PROF_DECL;
-            for (int64_t w = blockIdx.x; w < n_items; w += gridDim.x) {
+            for (uint32_t it = 0;; it++) {
+                const uint32_t is = it & 3u, ip = (it >> 2) & 1u;
+                if (!mbar_wait(BAR_IEMPTY + 8u * is, ip ^ 1u, abort_flag, 11)) break;
+                const int64_t w = atomicAdd(a.item_ctr, 1);
+                *(volatile int *)&item_ring[is] = (int)w;
+                mbar_arrive(BAR_IFULL + 8u * is);
+                if (w >= n_items) break;
                 const int chunk = (int)(w / a.owner_tiles);
                 const int64_t t0 = a.step_begin + (int64_t)chunk * a.chunk_steps;
                 const int nst = (int)min((int64_t)a.chunk_steps, a.step_end - t0);
@@ -633,9 +658,9 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
             uint32_t s_stage = 0, s_phase = 0;   // smem ring position of the next tile to run stage 1 on
             uint32_t slot = 0, use_par = 0;      // S slot of the next step and parity of its use count
             uint32_t g4 = 0;                     // step % 4: the epilogue group that takes the step
-            uint32_t u_phase = 0;
+            uint32_t u_phase = 0, item_no = 0;
             PROF_DECL;
-            for (int64_t w = blockIdx.x; w < n_items; w += gridDim.x) {
+            for (int64_t w; (w = take_item(item_no, 12)) >= 0;) {
                 const int chunk = (int)(w / a.owner_tiles);
                 const int64_t t0 = a.step_begin + (int64_t)chunk * a.chunk_steps;
                 const int nst = (int)min((int64_t)a.chunk_steps, a.step_end - t0);
@@ -682,9 +707,9 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
             constexpr uint32_t DLO2 = ((uint32_t)C::BLOCK_BYTES >> 4) << 16; // MN-major: LBO = k-block stride
             uint32_t g_stage = 0;                // smem ring position of the next tile to run stage 2 on
             uint32_t gs = 0;                     // global step counter
-            uint32_t u_phase = 0;
+            uint32_t u_phase = 0, item_no = 0;
             PROF_DECL;
-            for (int64_t w = blockIdx.x; w < n_items; w += gridDim.x) {
+            for (int64_t w; (w = take_item(item_no, 13)) >= 0;) {
                 const int chunk = (int)(w / a.owner_tiles);
                 const int64_t t0 = a.step_begin + (int64_t)chunk * a.chunk_steps;
                 const int nst = (int)min((int64_t)a.chunk_steps, a.step_end - t0);
@@ -762,7 +787,8 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
                     *reinterpret_cast<uint4 *>(dst + i) = make_uint4(r[i], r[i + 1], r[i + 2], r[i + 3]);
             }
         };
-        for (int64_t w = blockIdx.x; w < n_items && ok; w += gridDim.x) {
+        uint32_t item_no = 0;
+        for (int64_t w; ok && (w = take_item(item_no, 14)) >= 0;) {
             const int chunk = (int)(w / a.owner_tiles);
             const int64_t tile = a.tile_begin + w % a.owner_tiles;
             const int64_t t0 = a.step_begin + (int64_t)chunk * a.chunk_steps;
@@ -988,7 +1014,7 @@ static void tp_base_args(nbmf_handle *h, TPState *s, int owner_rows, bool want_l
     }
     a.owner_tiles_total = (a.L + 127) / 128;
     stream_steps = (S_rows + 63) / 64;
-    a.dexp = s->dexp; a.dacc = s->dacc; a.derr = s->derr;
+    a.dexp = s->dexp; a.dacc = s->dacc; a.derr = s->derr; a.item_ctr = s->item_ctr;
     a.want_log = want_log;
     // AUTO: the W_lo term of stage 2 buys ~5x accuracy at 10^3..10^4 rows/columns, but its benefit
     // falls like 1/sqrt(reduction length): at 262144^2 hi-only is within 1.6x of hi+lo and both are
@@ -1021,6 +1047,7 @@ static int tp_launch(nbmf_handle *h, TPState *s, int owner_rows, const TPArgs &a
     const int64_t items = (int64_t)a.n_chunks * a.owner_tiles;
     if (items <= 0) return NBMF_OK;
     const int grid = (int)std::min<int64_t>(items, h->sm_count);
+    if (cudaMemsetAsync(s->item_ctr, 0, 4, h->stream) != cudaSuccess) { h->err = "tp_pass: work counter reset failed"; return NBMF_ERR_CUDA; }
     // the mask plane is skipped only when there is no NA and no padding anywhere (padded lanes /
     // streamed rows rely on the mask bits being zero)
     const bool use_mask = h->has_na || (h->F % 128 != 0) || (h->N % 64 != 0);

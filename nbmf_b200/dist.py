@@ -29,9 +29,24 @@ def tensor_from_device_ptr(ptr: int, count: int, device):
     return torch.as_tensor(a, device=device)
 
 
+def init_nccl(device):
+    """`init_process_group("nccl")` with the collective stream at high priority: the engine overlaps the
+    exchange with its persistent cols-pass kernel, so the all-reduce's CTAs have to be placed first."""
+    import torch.distributed as dist
+    opts = None
+    try:
+        opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+    except Exception:  # older torch: default priority still works, with less overlap
+        opts = None
+    if opts is not None:
+        dist.init_process_group("nccl", device_id=device, pg_options=opts)
+    else:
+        dist.init_process_group("nccl", device_id=device)
+
+
 def make_allreduce_hook(device, group=None):
-    """Hook for Engine.set_allreduce_hook: sums the buffer across ranks in place,
-    ordered on the engine's stream."""
+    """Hook for Engine.set_allreduce_hook: sums the buffer across ranks in place, ordered on the
+    stream the engine passes (its main stream, or the side stream of an overlapped exchange)."""
     import torch
     import torch.distributed as dist
 

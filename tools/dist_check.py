@@ -8,12 +8,12 @@ import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from nbmf_b200 import Engine, _lib  # noqa: E402
-from nbmf_b200.dist import combine_lowerbounds, make_allreduce_hook, shard_columns  # noqa: E402
+from nbmf_b200.dist import combine_lowerbounds, init_nccl, make_allreduce_hook, shard_columns  # noqa: E402
 
 rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
-dist.init_process_group("nccl", device_id=dev)
+init_nccl(dev)
 rel = lambda x, y: np.linalg.norm(x - y) / np.linalg.norm(y)
 for (F, N, K, prec, iters) in [(300, 1000, 5, _lib.PREC_FP64, 12), (2048, 4096, 128, _lib.PREC_TENSOR, 8), (1500, 3000, 64, _lib.PREC_AUTO, 6)]:
     lo, hi = shard_columns(N, rank, world)

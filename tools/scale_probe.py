@@ -3,10 +3,10 @@ import os, sys, time
 import torch, torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from nbmf_b200 import Engine
-from nbmf_b200.dist import make_allreduce_hook, shard_columns
+from nbmf_b200.dist import init_nccl, make_allreduce_hook, shard_columns
 rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local); dev = torch.device("cuda", local)
-dist.init_process_group("nccl", device_id=dev)
+init_nccl(dev)
 F = N = 262144; K = 128
 lo, hi = shard_columns(N, rank, world)
 e = Engine(device=local, n_global=N, n_offset=lo)
