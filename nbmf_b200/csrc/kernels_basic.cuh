@@ -92,6 +92,17 @@ transpose_bits_kernel(const uint32_t *__restrict__ src, int64_t R, int64_t Ws,
     }
 }
 
+// a bounded pause on the stream (no flag is polled): lets a kernel that another stream has just
+// been allowed to start get its CTAs placed before the next persistent kernel takes every SM
+__global__ void pause_kernel(unsigned ns)
+{
+    const long long t0 = clock64();
+    for (unsigned waited = 0; waited < ns; waited += 1000) {
+        __nanosleep(1000);
+        if (clock64() - t0 > (long long)ns * 4) break;   // never more than ~ns at >= 250 MHz
+    }
+}
+
 __global__ void popcount_kernel(const uint32_t *__restrict__ m, int64_t count, unsigned long long *out)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

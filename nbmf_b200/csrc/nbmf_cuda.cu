@@ -185,6 +185,14 @@ static int exchange_begin(nbmf_handle *h, double *buf, size_t count)
     if (rc != 0) return fail(h, NBMF_ERR_CUDA, "all-reduce hook failed");
     CK(cudaEventRecord(h->xchg_ev[1], h->xchg_stream));
     h->xchg_pending = true;
+    // The collective's kernel and the cols pass become runnable at the same moment; if the
+    // persistent cols kernel is placed first it holds every SM and the collective runs after it
+    // instead of beside it.  20 us on the main stream decide that race (NBMF_XCHG_PAUSE_US).
+    static const int pause_us = [] { const char *v = getenv("NBMF_XCHG_PAUSE_US"); return v ? atoi(v) : 20; }();
+    if (pause_us > 0) {
+        pause_kernel<<<1, 32, 0, h->stream>>>((unsigned)pause_us * 1000u);
+        LAUNCH_CHECK();
+    }
     h->timing.launches += 1;
     return NBMF_OK;
 }
