@@ -73,8 +73,11 @@ typedef struct nbmf_handle nbmf_handle;
 
 /* collective hook: called on the exchange step of each iteration with a device
  * buffer the caller must sum across ranks in place (count elements of fp64),
- * enqueued on `stream` (a cudaStream_t).  Return 0 on success.  This is the only
- * data-path collective: the F x K Dirichlet-side statistic.     */
+ * enqueued on `stream` (a cudaStream_t) -- the handle's own stream, or, on the
+ * tensor path, a priority side stream so that the collective overlaps the second
+ * pass; the hook must order its work on the stream it is given and not
+ * synchronise the device.  Return 0 on success.  This is the only data-path
+ * collective: the F x K Dirichlet-side statistic.               */
 typedef int (*nbmf_allreduce_fn)(void *ctx, void *device_buf, size_t count, void *stream);
 
 /* timing of the last VB / Gibbs call, CUDA events on the handle's stream */

@@ -161,9 +161,6 @@ static int exchange(nbmf_handle *h, double *buf, size_t count)
     return NBMF_OK;
 }
 
-// ---------------------------------------------------------------------------
-// data
-// ---------------------------------------------------------------------------
 // The same exchange started on a side stream behind the current point of the main stream, so
 // that whatever the main stream launches next overlaps it; exchange_end makes the main stream
 // wait for the result.  The side stream has the highest priority: the collective's few CTAs are
@@ -204,6 +201,9 @@ static int exchange_end(nbmf_handle *h)
     return NBMF_OK;
 }
 
+// ---------------------------------------------------------------------------
+// data
+// ---------------------------------------------------------------------------
 static int alloc_planes(nbmf_handle *h, int64_t F, int64_t N)
 {
     CK(cudaSetDevice(h->device));
