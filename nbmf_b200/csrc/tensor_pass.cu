@@ -1,11 +1,11 @@
 // tensor_pass.cu -- the tcgen05 / TMEM / TMA contraction pass of libnbmf_cuda.
 //
 // One kernel serves both statistics ("owner / stream" form, see kernels_basic.cuh):
-//   owner lane l (128 per CTA tile, = TMEM lane)  operand u_l   (f16 hi + lo, in TMEM)
-//   streamed row c (256 per step, via TMA)        operand w_c   (f16 hi, in smem)
-//   stage 1   S[l][c]  = u_l . w_c   (hi parts only)      tcgen05.mma TS, fp32 in TMEM
-//   epilogue  R[l][c]  = sel(l,c) / S[l][c]  -> f16, written back over S in TMEM
-//   stage 2   G[l][:] += sum_c R[l][c] (w_hi + w_lo)_c    2 x tcgen05.mma TS, B operand MN-major
+//   owner lane l (128 per CTA tile, = TMEM lane)  operand u_l   (f16 hi, in TMEM)
+//   streamed row c (64 per step, via TMA)         operand w_c   (f16 hi [+ lo], in smem)
+//   stage 1   S[l][c]  = u_l . w_c   (hi parts only)      tcgen05.mma TS, fp32 in a TMEM S slot
+//   epilogue  R[l][c]  = sel(l,c) / S[l][c]  -> f16, written to a TMEM R slot
+//   stage 2   G[l][:] += sum_c R[l][c] (w_hi [+ w_lo])_c  tcgen05.mma TS, B operand MN-major
 // rows pass: owner = row f (u = A_f), stream = (n,b) pairs (w = B_b(n,:)), sel = mask & (v==b)
 // cols pass: owner = (n,b) lane (u = B_b(n,:)), stream = row f (w = A_f), same sel.
 //
@@ -13,19 +13,21 @@
 // emulation): S only feeds R = 1/S, whose relative error is an average over k of the
 // operands' f16 rounding errors and largely cancels against the numerator -- one f16 pass
 // is enough.  The numerator (stage 2) carries the streamed operand's rounding error
-// directly into the statistic, so there the operand is split hi+lo (22 bits).  R is a
+// directly into the statistic, so there the operand is split hi+lo (22 bits) unless the
+// reduction is long enough for hi alone (AUTO policy in tp_base_args).  R is a
 // single f16 (its error is independent per entry and averages over the reduction).  All
 // accumulation is fp32 in TMEM over a bounded chunk of steps; chunk partials are summed
 // in fp64, and each statistic row is rescaled to its exact observation count
 // (tp_finalize_kernel), which removes the round-toward-zero bias of the tensor pipe's
 // accumulator.
 //
-// Work decomposition: item = (stream chunk, owner tile); persistent CTAs take items
-// round-robin with the owner tile fastest, so the CTAs running at any time stream
-// the SAME chunk (served once from HBM, then from L2).
+// Work decomposition: item = (stream chunk, owner tile), owner tile fastest; persistent CTAs
+// pull items from a global queue, so the CTAs running at any time stream the SAME chunk
+// (served once from HBM, then from L2) and a CTA that starts late takes fewer items.
 //
-// Warp roles (384 threads): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM
-// allocator, warps 4-7 epilogue of column-half 0, warps 8-11 epilogue of half 1.
+// Warp roles (640 threads): warp 0 TMA producer + item fetcher, warp 1 stage-1 issuer,
+// warp 2 TMEM allocator, warp 3 stage-2 issuer, warps 4-19 four epilogue warpgroups (the
+// pipeline and its barriers are described above TPCfg).
 #include "tensor_pass.h"
 #include <cuda.h>
 #include <cuda_fp16.h>
