@@ -24,6 +24,8 @@ def _case(F, N, Kt, K, na, seed):
     (100, 400, 4, 10, 0.1, 9, 0.3),      # NA entries (unvotes-like), K = 10
     (37, 53, 2, 5, 0.2, 8, 0.0),         # ragged, burnin 0: every sweep kept, first slice stays zero (i starts at 1)
     (1100, 1200, 4, 4, 0.05, 3, 0.5),    # diagonals longer than one block: cooperative grid barrier
+    (48, 70, 3, 40, 0.1, 5, 0.4),        # K = 40 > 32: lanes of a group take several k
+    (300, 40, 3, 17, 0.0, 4, 0.5),       # 32 lanes per entry, several passes of one block per diagonal
 ])
 def test_collapsed_sweep_is_bit_exact(F, N, Kt, K, na, iter, burnin):
     from nbmf_b200 import Engine, _lib

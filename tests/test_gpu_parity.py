@@ -159,7 +159,9 @@ def test_vb_resume_from_statistics_checkpoint():
 # VB_DirBer_Rcpp
 # ---------------------------------------------------------------------------
 @pytest.mark.parametrize("F,N,K,na,iters", [(200, 300, 3, 0.0, 30), (23, 31, 4, 0.2, 12), (100, 543, 10, 0.2, 6),
-                                            (9, 40, 3, 0.0, 12), (33, 8, 2, 0.4, 12)])
+                                            (9, 40, 3, 0.0, 12), (33, 8, 2, 0.4, 12),
+                                            (48, 70, 39, 0.1, 4),     # Kc = 40 > 32: lanes of a group take several k
+                                            (300, 40, 16, 0.0, 4)])   # Kc = 17, diagonal x lanes > one block pass
 def test_vb_dirber_wavefront_bit_identical(F, N, K, na, iters):
     from nbmf_b200 import VB_DirBer_Rcpp
     V = make_problem(F, N, 3, 17, na)
