@@ -211,6 +211,21 @@ int nbmf_gibbs_dirber_collapsed(nbmf_handle *h, int K, double alpha, double beta
                                 double burnin, uint64_t seed, int32_t *Z_samples, int *n_samples_written,
                                 int32_t *Z_last);
 
+/* ---- Gibbs_DirBer_DP_Rcpp (collapsed_gibbs_z.cpp:275-359) and Gibbs_DirDir_finite_Rcpp
+ * (:441-557), the sibling collapsed samplers, same wavefront + keyed-uniform scheme and the same
+ * bit-exact parity bar (oracle_gibbs_dirber_dp_keyed / oracle_gibbs_dirdir_keyed).
+ * DP: Kmax = 200 components (:282) -- install the labels with nbmf_init_from_labels(Z, 200);
+ * alpha and beta are ignored as in the reference (its Beta prior is epsilon = 1e-8, :281);
+ * V must be fully observed (the reference has no NA test there, :308-310).
+ * Dir-Dir: a second assignment matrix C (initialised to Z, :465); C_samples / C_last like the
+ * Z outputs; K >= 2.                                                              */
+int nbmf_gibbs_dirber_dp_collapsed(nbmf_handle *h, double alpha, double beta, double gamma, int iter,
+                                   double burnin, uint64_t seed, int32_t *Z_samples, int *n_samples_written,
+                                   int32_t *Z_last);
+int nbmf_gibbs_dirdir_collapsed(nbmf_handle *h, int K, double alpha, double gamma, int iter, double burnin,
+                                uint64_t seed, int32_t *Z_samples, int32_t *C_samples, int *n_samples_written,
+                                int32_t *Z_last, int32_t *C_last);
+
 /* one column's sweep given a fixed dictionary (sample_gibbs.cpp:22-80,
  * R sample_gibbs_ZH): v_n[F] in {0,1}, W F x K (paper orientation: Beta means),
  * returns the mean one-hot assignment C_mean F x K over kept sweeps.          */

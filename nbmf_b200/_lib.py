@@ -70,6 +70,10 @@ SYMBOLS = {
                                     C.c_uint64, _dp, _dp, _lp, C.c_int64, _dp, _ip]),
     "nbmf_gibbs_dirber_collapsed": (C.c_int, [_H, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_double,
                                               C.c_uint64, _ip, C.POINTER(C.c_int), _ip]),
+    "nbmf_gibbs_dirber_dp_collapsed": (C.c_int, [_H, C.c_double, C.c_double, C.c_double, C.c_int, C.c_double,
+                                                 C.c_uint64, _ip, C.POINTER(C.c_int), _ip]),
+    "nbmf_gibbs_dirdir_collapsed": (C.c_int, [_H, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_uint64,
+                                              _ip, _ip, C.POINTER(C.c_int), _ip, _ip]),
     "nbmf_gibbs_sweep_given_W": (C.c_int, [_H, _ip, _dp, C.c_int64, C.c_int, C.c_double, C.c_int, C.c_double,
                                            C.c_uint64, _dp]),
     "nbmf_predictive_ll": (C.c_int, [_H, _dp, _dp, C.c_int, _ip, C.c_int64, C.c_int64, _dp, _lp]),

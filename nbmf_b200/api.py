@@ -263,6 +263,29 @@ class Engine:
                                                       C.byref(nw), _ptr(Zl, _ip)))
         return (Zs[:, :, :ns] if want_samples else None), nw.value, Zl
 
+    def gibbs_dirber_dp_collapsed(self, gamma=1.0, iter=100, burnin=0.5, seed=1, want_samples=True):
+        """Gibbs_DirBer_DP_Rcpp's sweep (Kmax = 200; labels installed with init_from_labels(Z, 200))."""
+        ns = iter - int(np.floor(iter * burnin))
+        Zs = np.zeros((self.F, self.N, max(ns, 1)), dtype=np.int32, order="F") if want_samples else None
+        Zl = np.zeros((self.F, self.N), dtype=np.int32, order="F")
+        nw = C.c_int(0)
+        self._ck(self.lib.nbmf_gibbs_dirber_dp_collapsed(self.h, 1.0, 1.0, gamma, iter, burnin, seed, _ptr(Zs, _ip),
+                                                         C.byref(nw), _ptr(Zl, _ip)))
+        return (Zs[:, :, :ns] if want_samples else None), nw.value, Zl
+
+    def gibbs_dirdir_collapsed(self, K, alpha=1.0, gamma=1.0, iter=100, burnin=0.5, seed=1, want_samples=True):
+        """Gibbs_DirDir_finite_Rcpp's sweep: assignments Z and C."""
+        ns = iter - int(np.floor(iter * burnin))
+        mk = lambda: np.zeros((self.F, self.N, max(ns, 1)), dtype=np.int32, order="F")
+        Zs, Cs = (mk(), mk()) if want_samples else (None, None)
+        Zl = np.zeros((self.F, self.N), dtype=np.int32, order="F"); Cl = np.zeros_like(Zl, order="F")
+        nw = C.c_int(0)
+        self._ck(self.lib.nbmf_gibbs_dirdir_collapsed(self.h, K, alpha, gamma, iter, burnin, seed, _ptr(Zs, _ip),
+                                                      _ptr(Cs, _ip), C.byref(nw), _ptr(Zl, _ip), _ptr(Cl, _ip)))
+        if want_samples:
+            Zs, Cs = Zs[:, :, :ns], Cs[:, :, :ns]
+        return Zs, Cs, nw.value, Zl, Cl
+
     def gibbs_sweep_given_W(self, v_n, W, alpha=1.0, iter=100, burnin=0.5, seed=1):
         v = np.ascontiguousarray(v_n, dtype=np.int32)
         W = np.asfortranarray(W, dtype=np.float64)
@@ -352,6 +375,30 @@ def Gibbs_DirBer_finite_Rcpp(V, Z, K, alpha=1.0, beta=1.0, gamma=1.0, iter=100, 
         if own:
             e.close()
     return {"E_W": E_W, "E_H": E_H, "E_V_test": E_V, "Z_last": Zl}
+
+
+def Gibbs_DirBer_DP_Rcpp(V, Z, alpha=1.0, beta=1.0, gamma=1.0, iter=100, burnin=0.5, *, seed=1, engine=None, device=0):
+    """collapsed_gibbs_z.cpp:275-359 (Kmax = 200, `alpha` / `beta` unused there).  Returns `Z_samples`."""
+    e, own = _engine_for(V, engine, device=device, precision=_lib.PREC_FP64)
+    try:
+        e.init_from_labels(Z, 200)
+        Zs, nw, Zl = e.gibbs_dirber_dp_collapsed(gamma, iter, burnin, seed)
+    finally:
+        if own:
+            e.close()
+    return {"Z_samples": Zs, "Z_last": Zl, "written": nw}
+
+
+def Gibbs_DirDir_finite_Rcpp(V, Z, K, alpha=1.0, gamma=1.0, iter=100, burnin=0.5, *, seed=1, engine=None, device=0):
+    """collapsed_gibbs_z.cpp:441-557.  Returns `Z_samples` and `C_samples`."""
+    e, own = _engine_for(V, engine, device=device, precision=_lib.PREC_FP64)
+    try:
+        e.init_from_labels(Z, K)
+        Zs, Cs, nw, Zl, Cl = e.gibbs_dirdir_collapsed(K, alpha, gamma, iter, burnin, seed)
+    finally:
+        if own:
+            e.close()
+    return {"Z_samples": Zs, "C_samples": Cs, "Z_last": Zl, "C_last": Cl, "written": nw}
 
 
 def lower_bound_aspect(V, n_total, f_ones, f_zeros, alpha, beta, gamma, *, device=0):

@@ -596,9 +596,44 @@ struct GibbsWaveArgs {
     int32_t *cN;         // [2N][K]     row 2n+1 f_ones, row 2n f_zeros
     int32_t *Z_samples;  // [nsamples][N][F] or NULL (:423-426)
     int *n_written;
+    // Dir-Dir only: the second assignment C with its own counts
+    int32_t *C, *cF2, *cN2, *C_samples;
 };
 
-template <bool SINGLE_BLOCK, int G>
+// Categorical draw shared by the G lanes of a group: q(k) is the unnormalised weight of
+// component k.  s = sum_k q(k) and the inverse-CDF scan over q(k)/s are accumulated in the
+// order k = 0, 1, ... (shuffles carry the running sums), exactly as probs/accu(probs) followed
+// by a sequential scan would; every lane returns the same k.
+template <int G, typename QF>
+__device__ __forceinline__ int group_draw(int K, int gl, int gbase, double u, QF q)
+{
+    double s = 0.0;
+    for (int k0 = 0; k0 < K; k0 += G) {
+        const int k = k0 + gl;
+        const double qk = k < K ? q(k) : 0.0;
+        const int kn = K - k0 < G ? K - k0 : G;
+        for (int j = 0; j < kn; j++) s = __dadd_rn(s, __shfl_sync(0xffffffffu, qk, gbase + j));
+    }
+    double c = 0.0;
+    int k1 = -1, last_pos = K - 1;
+    for (int k0 = 0; k0 < K; k0 += G) {
+        const int k = k0 + gl;
+        const double pr = k < K ? __ddiv_rn(q(k), s) : 0.0;
+        const int kn = K - k0 < G ? K - k0 : G;
+        for (int j = 0; j < kn; j++) {
+            const double pj = __shfl_sync(0xffffffffu, pr, gbase + j);
+            c = __dadd_rn(c, pj);
+            if (pj > 0.0) last_pos = k0 + j;
+            if (k1 < 0 && u < c) k1 = k0 + j;
+        }
+    }
+    return k1 < 0 ? last_pos : k1;
+}
+
+// VARIANT 0: Gibbs_DirBer_finite_Rcpp (collapsed_gibbs_z.cpp:363-437)
+//         1: Gibbs_DirBer_DP_Rcpp     (:275-359; K = 200, V without NA)
+//         2: Gibbs_DirDir_finite_Rcpp (:441-557; assignments Z and C)
+template <bool SINGLE_BLOCK, int G, int VARIANT>
 __global__ void __launch_bounds__(1024) gibbs_collapsed_wavefront_kernel(GibbsWaveArgs a)
 {
     cg::grid_group grid = cg::this_grid();
@@ -626,58 +661,90 @@ __global__ void __launch_bounds__(1024) gibbs_collapsed_wavefront_kernel(GibbsWa
                     act = (mw >> (f & 31)) & 1u;
                     v = (a.vc[n * a.Fw + (f >> 5)] >> (f & 31)) & 1u;
                 }
+                // inactive groups run the arithmetic on row 0 and store nothing
                 const int64_t fs = act ? f : 0, ns = act ? n : 0;
                 int32_t *nF = a.cF + fs * K, *nV = a.cN + (2 * ns + v) * K;
                 const int32_t *n1 = a.cN + (2 * ns + 1) * K, *n0 = a.cN + (2 * ns) * K;
                 const int k_old = act ? a.Z[fs + F * ns] : -1;
-                // probabilities with the entry's own assignment removed (:396-407); the counts in
-                // memory are only touched once, at the end, by the group's first lane
-                auto prob = [&](int k) {
-                    const int own = (k == k_old) ? 1 : 0;
-                    const double gp = __dadd_rn(a.gamma, (double)(nF[k] - own));
-                    const double ap = __dadd_rn(a.alpha, (double)(n1[k] - (v ? own : 0)));
-                    const double bp = __dadd_rn(a.beta, (double)(n0[k] - (v ? 0 : own)));
-                    return __ddiv_rn(__dmul_rn(gp, v ? ap : bp), __dadd_rn(ap, bp));
-                };
-                double s = 0.0;
-                for (int k0 = 0; k0 < K; k0 += G) {
-                    const int k = k0 + gl;
-                    const double q = k < K ? prob(k) : 0.0;
-                    const int kn = K - k0 < G ? K - k0 : G;
-                    for (int j = 0; j < kn; j++) s = __dadd_rn(s, __shfl_sync(0xffffffffu, q, gbase + j));
-                }
                 const philox4 r = philox4x32_10((uint32_t)fs, (uint32_t)ns, (uint32_t)i, 0u, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
-                const double u = u64_to_unif(r.x, r.y);
-                double c = 0.0;
-                int k1 = -1, last_pos = K - 1;
-                for (int k0 = 0; k0 < K; k0 += G) {   // :408, inverse CDF in place of rmultinom + index_max (:411-413)
-                    const int k = k0 + gl;
-                    const double pr = k < K ? __ddiv_rn(prob(k), s) : 0.0;
-                    const int kn = K - k0 < G ? K - k0 : G;
-                    for (int j = 0; j < kn; j++) {
-                        const double pj = __shfl_sync(0xffffffffu, pr, gbase + j);
-                        c = __dadd_rn(c, pj);
-                        if (pj > 0.0) last_pos = k0 + j;
-                        if (k1 < 0 && u < c) k1 = k0 + j;
+                const double u0 = u64_to_unif(r.x, r.y);
+                // The counts in memory are touched once, at the end, by the group's first lane; until
+                // then "the entry's own assignment removed" (:396) is a -1 on the component it holds.
+                if (VARIANT == 0) {
+                    const int k1 = group_draw<G>(K, gl, gbase, u0, [&](int k) {   // :402-408
+                        const int own = (k == k_old) ? 1 : 0;
+                        const double gp = __dadd_rn(a.gamma, (double)(nF[k] - own));
+                        const double ap = __dadd_rn(a.alpha, (double)(n1[k] - (v ? own : 0)));
+                        const double bp = __dadd_rn(a.beta, (double)(n0[k] - (v ? 0 : own)));
+                        return __ddiv_rn(__dmul_rn(gp, v ? ap : bp), __dadd_rn(ap, bp));
+                    });
+                    if (act && gl == 0) {
+                        nF[k_old] -= 1; nV[k_old] -= 1;   // remove_assignment (:75-85)
+                        a.Z[fs + F * ns] = k1;            // set_assignment (:63-72)
+                        nF[k1] += 1; nV[k1] += 1;
                     }
-                }
-                if (k1 < 0) k1 = last_pos;
-                if (act && gl == 0) {
-                    nF[k_old] -= 1; nV[k_old] -= 1;   // remove_assignment (:75-85)
-                    a.Z[fs + F * ns] = k1;            // set_assignment (:63-72)
-                    nF[k1] += 1; nV[k1] += 1;
+                } else if (VARIANT == 1) {
+                    // first empty component of row f (:325-328), found chunk by chunk with a ballot
+                    int k_free = -1;
+                    for (int k0 = 0; k0 < K; k0 += G) {   // every lane of the warp takes every ballot
+                        const int k = k0 + gl;
+                        const bool empty = k < K && (nF[k] - (k == k_old ? 1 : 0)) == 0;
+                        const uint32_t m = (__ballot_sync(0xffffffffu, empty) >> gbase) & (G == 32 ? 0xffffffffu : ((1u << G) - 1u));
+                        if (m && k_free < 0) k_free = k0 + __ffs(m) - 1;
+                    }
+                    const int k1 = group_draw<G>(K, gl, gbase, u0, [&](int k) {   // :317-329
+                        if (k == k_free) return __dmul_rn(a.gamma, 0.5);
+                        const int own = (k == k_old) ? 1 : 0;
+                        const double ap = __dadd_rn((double)(n1[k] - (v ? own : 0)), 1e-8);
+                        const double bp = __dadd_rn((double)(n0[k] - (v ? 0 : own)), 1e-8);
+                        return __dmul_rn((double)(nF[k] - own), __ddiv_rn(v ? ap : bp, __dadd_rn(ap, bp)));
+                    });
+                    if (act && gl == 0) {
+                        nF[k_old] -= 1; nV[k_old] -= 1;
+                        a.Z[fs + F * ns] = k1;
+                        nF[k1] += 1; nV[k1] += 1;
+                    }
+                } else {
+                    int32_t *cF2 = a.cF2 + fs * K, *cV2 = a.cN2 + (2 * ns + v) * K;
+                    const int32_t *c1 = a.cN2 + (2 * ns + 1) * K, *c0 = a.cN2 + (2 * ns) * K;
+                    const int c_old = act ? a.C[fs + F * ns] : -1;
+                    const double u1 = u64_to_unif(r.z, r.w);
+                    // Both draws are executed by every group (the shuffles need the whole warp); which
+                    // formula a group uses, and whether it keeps the second draw, depends on its v.
+                    // V = 1: Z and C together from (gamma + n^Z_f)(alpha + t^C_n) (:481-497).
+                    // V = 0: Z with C's component forbidden, then C with the new Z component forbidden (:500-531).
+                    const int kz = group_draw<G>(K, gl, gbase, u0, [&](int k) {
+                        const double gp = __dadd_rn(a.gamma, (double)(nF[k] - (k == k_old ? 1 : 0)));
+                        if (v) return __dmul_rn(gp, __dadd_rn(a.alpha, (double)(c1[k] + c0[k] - (k == c_old ? 1 : 0))));
+                        return k == c_old ? 0.0 : gp;
+                    });
+                    const int kc2 = group_draw<G>(K, gl, gbase, u1, [&](int k) {
+                        return k == kz ? 0.0 : __dadd_rn(a.alpha, (double)(c1[k] + c0[k] - (k == c_old ? 1 : 0)));
+                    });
+                    const int kc = v ? kz : kc2;
+                    if (act && gl == 0) {
+                        nF[k_old] -= 1; nV[k_old] -= 1; cF2[c_old] -= 1; cV2[c_old] -= 1;
+                        a.Z[fs + F * ns] = kz; a.C[fs + F * ns] = kc;
+                        nF[kz] += 1; nV[kz] += 1; cF2[kc] += 1; cV2[kc] += 1;
+                    }
                 }
             }
             if (SINGLE_BLOCK) __syncthreads();
             else grid.sync();
         }
-        if (i >= a.nburnin && a.Z_samples && jw < a.nsamples) {   // :423-426
-            int32_t *dst = a.Z_samples + (int64_t)jw * F * N;
-            for (int64_t e = tid; e < F * N; e += nthreads) dst[e] = a.Z[e];
+        if (i >= a.nburnin && jw < a.nsamples) {   // :423-426
+            if (a.Z_samples) {
+                int32_t *dst = a.Z_samples + (int64_t)jw * F * N;
+                for (int64_t e = tid; e < F * N; e += nthreads) dst[e] = a.Z[e];
+                if (VARIANT == 2 && a.C_samples) {
+                    int32_t *dc = a.C_samples + (int64_t)jw * F * N;
+                    for (int64_t e = tid; e < F * N; e += nthreads) dc[e] = a.C[e];
+                }
+                if (SINGLE_BLOCK) __syncthreads();
+                else grid.sync();
+            }
             jw++;
-            if (SINGLE_BLOCK) __syncthreads();
-            else grid.sync();
-        } else if (i >= a.nburnin && jw < a.nsamples) jw++;
+        }
     }
     if (tid == 0) *a.n_written = jw;
 }

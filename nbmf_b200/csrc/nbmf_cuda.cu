@@ -910,9 +910,11 @@ template <bool SB, int G> struct Cvb0Kern {
     static void *ptr() { return (void *)cvb0_wavefront_kernel<SB, G>; }
     static void launch(WaveArgs &a, int blocks, int threads, cudaStream_t st) { cvb0_wavefront_kernel<SB, G><<<blocks, threads, 0, st>>>(a); }
 };
-template <bool SB, int G> struct GibbsWaveKern {
-    static void *ptr() { return (void *)gibbs_collapsed_wavefront_kernel<SB, G>; }
-    static void launch(GibbsWaveArgs &a, int blocks, int threads, cudaStream_t st) { gibbs_collapsed_wavefront_kernel<SB, G><<<blocks, threads, 0, st>>>(a); }
+template <int VARIANT> struct GibbsWave {
+    template <bool SB, int G> struct Kern {
+        static void *ptr() { return (void *)gibbs_collapsed_wavefront_kernel<SB, G, VARIANT>; }
+        static void launch(GibbsWaveArgs &a, int blocks, int threads, cudaStream_t st) { gibbs_collapsed_wavefront_kernel<SB, G, VARIANT><<<blocks, threads, 0, st>>>(a); }
+    };
 };
 
 static int dirber_wavefront(nbmf_handle *h, int K, double alpha, double beta, double gamma, int iter,
@@ -1131,28 +1133,33 @@ extern "C" int nbmf_gibbs_dirber(nbmf_handle *h, int K, double alpha, double bet
     return rc;
 }
 
-// Gibbs_DirBer_finite_Rcpp (collapsed_gibbs_z.cpp:363-437) with its own schedule: the collapsed
-// sweep in anti-diagonal wavefront order, uniforms keyed (seed; f, n, sweep).  Sized for the
-// configurations the reference itself can run (labels + Z_samples on the device); replicas only.
-extern "C" int nbmf_gibbs_dirber_collapsed(nbmf_handle *h, int K, double alpha, double beta, double gamma,
-                                           int iter, double burnin, uint64_t seed, int32_t *Z_samples,
-                                           int *n_samples_written, int32_t *Z_last)
+// The reference's collapsed samplers with their own schedule: the sequential sweep in anti-diagonal
+// wavefront order, uniforms keyed (seed; f, n, sweep).  variant 0 = Gibbs_DirBer_finite_Rcpp
+// (collapsed_gibbs_z.cpp:363-437), 1 = Gibbs_DirBer_DP_Rcpp (:275-359), 2 = Gibbs_DirDir_finite_Rcpp
+// (:441-557).  Sized for the configurations the reference itself can run (labels and the sample
+// cubes live on the device); replicas only.
+static int collapsed_wavefront(nbmf_handle *h, int variant, int K, double alpha, double beta, double gamma,
+                               int iter, double burnin, uint64_t seed, int32_t *Z_samples, int32_t *C_samples,
+                               int *n_samples_written, int32_t *Z_last, int32_t *C_last)
 {
-    if (!h) return NBMF_ERR_ARG;
     if (!h->vc) return fail(h, NBMF_ERR_STATE, "no data");
     if (K <= 0 || iter < 0 || !(alpha > 0) || !(beta > 0) || !(gamma > 0) || !(burnin >= 0) || burnin > 1)
-        return fail(h, NBMF_ERR_ARG, "nbmf_gibbs_dirber_collapsed: bad arguments");
+        return fail(h, NBMF_ERR_ARG, "collapsed sampler: bad arguments");
     if (!h->Z) return fail(h, NBMF_ERR_STATE, "the collapsed sweep needs labels: call nbmf_init_from_labels(Z, K)");
     if (h->hook) return fail(h, NBMF_ERR_UNSUPPORTED, "the collapsed wavefront sweep is replicas-only (no column sharding)");
+    if (variant == 1 && h->has_na)
+        return fail(h, NBMF_ERR_UNSUPPORTED, "Gibbs_DirBer_DP_Rcpp has no NA test (collapsed_gibbs_z.cpp:308-310): V must be fully observed");
+    if (variant == 2 && K < 2) return fail(h, NBMF_ERR_ARG, "Gibbs_DirDir_finite_Rcpp needs K >= 2 (a zero entry forbids one component)");
     CK(cudaSetDevice(h->device));
     const int64_t F = h->F, N = h->N;
     const int nburnin = (int)std::floor(iter * burnin);
     const int nsamples = iter - (int)std::floor(iter * burnin);
     const size_t slice = (size_t)F * N * 4;
-    const bool keep = Z_samples != nullptr && nsamples > 0;
-    if (keep && (double)slice * nsamples > 32e9)
-        return fail(h, NBMF_ERR_UNSUPPORTED, "Z_samples does not fit on the device: pass NULL (nbmf_gibbs_dirber returns the posterior means without it)");
-    int32_t *cF = nullptr, *cN = nullptr, *Zs = nullptr;
+    const bool two = variant == 2;
+    const bool keep = (Z_samples != nullptr || (two && C_samples != nullptr)) && nsamples > 0;
+    if (keep && (double)slice * nsamples * (two ? 2 : 1) > 32e9)
+        return fail(h, NBMF_ERR_UNSUPPORTED, "the sample cubes do not fit on the device: pass NULL (nbmf_gibbs_dirber returns the posterior means without them)");
+    int32_t *cF = nullptr, *cN = nullptr, *cF2 = nullptr, *cN2 = nullptr, *Zs = nullptr, *Cs = nullptr, *Cd = nullptr;
     int *nw = nullptr;
     unsigned long long *cnt = (unsigned long long *)h->scal + SC_TMP;
     const size_t fk = (size_t)F * K, nk = (size_t)2 * N * K;
@@ -1160,13 +1167,23 @@ extern "C" int nbmf_gibbs_dirber_collapsed(nbmf_handle *h, int K, double alpha, 
     if (e == cudaSuccess) e = cudaMalloc(&cN, nk * 4);
     if (e == cudaSuccess) e = cudaMalloc(&nw, 4);
     if (e == cudaSuccess && keep) e = cudaMalloc(&Zs, slice * nsamples);
+    if (e == cudaSuccess && two) e = cudaMalloc(&cF2, fk * 4);
+    if (e == cudaSuccess && two) e = cudaMalloc(&cN2, nk * 4);
+    if (e == cudaSuccess && two) e = cudaMalloc(&Cd, slice);
+    if (e == cudaSuccess && two && keep) e = cudaMalloc(&Cs, slice * nsamples);
     int rc = NBMF_OK;
     if (e == cudaSuccess) {
         cudaMemsetAsync(cF, 0, fk * 4, h->stream); cudaMemsetAsync(cN, 0, nk * 4, h->stream);
         cudaMemsetAsync(nw, 0, 4, h->stream); cudaMemsetAsync(cnt, 0, 16, h->stream);
         if (keep) cudaMemsetAsync(Zs, 0, slice * nsamples, h->stream);   // :380-381
+        if (two && keep) cudaMemsetAsync(Cs, 0, slice * nsamples, h->stream);
         counts_from_labels_kernel<<<nblk(F * N, 256), 256, 0, h->stream>>>(h->Z, h->vc, h->has_na ? h->mc : nullptr, F, N, h->Fw, K, cF, cN, cnt + 1);
         e = cudaGetLastError();
+        if (e == cudaSuccess && two) {   // C = Z, cnt_c = cnt_z (:465-473)
+            e = cudaMemcpyAsync(Cd, h->Z, slice, cudaMemcpyDeviceToDevice, h->stream);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(cF2, cF, fk * 4, cudaMemcpyDeviceToDevice, h->stream);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(cN2, cN, nk * 4, cudaMemcpyDeviceToDevice, h->stream);
+        }
         unsigned long long bad = 0;
         if (e == cudaSuccess) e = cudaMemcpyAsync(&bad, cnt + 1, 8, cudaMemcpyDeviceToHost, h->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
@@ -1180,25 +1197,59 @@ extern "C" int nbmf_gibbs_dirber_collapsed(nbmf_handle *h, int K, double alpha, 
         a.K = K; a.iter = iter; a.nburnin = nburnin; a.nsamples = nsamples;
         a.alpha = alpha; a.beta = beta; a.gamma = gamma; a.seed = seed;
         a.Z = h->Z; a.cF = cF; a.cN = cN; a.Z_samples = keep ? Zs : nullptr; a.n_written = nw;
-        e = launch_wavefront<GibbsWaveKern>(h, a, K, std::min(F, N));
+        a.C = Cd; a.cF2 = cF2; a.cN2 = cN2; a.C_samples = keep ? Cs : nullptr;
+        const int64_t diag = std::min(F, N);
+        if (variant == 0) e = launch_wavefront<GibbsWave<0>::Kern>(h, a, K, diag);
+        else if (variant == 1) e = launch_wavefront<GibbsWave<1>::Kern>(h, a, K, diag);
+        else e = launch_wavefront<GibbsWave<2>::Kern>(h, a, K, diag);
         h->timing.launches += 1;
     }
     cudaEventRecord(h->ev[6], h->stream);
     int written = 0;
     if (e == cudaSuccess && rc == NBMF_OK) {
         e = cudaMemcpyAsync(&written, nw, 4, cudaMemcpyDeviceToHost, h->stream);
-        if (e == cudaSuccess && keep) e = cudaMemcpyAsync(Z_samples, Zs, slice * nsamples, cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess && keep && Z_samples) e = cudaMemcpyAsync(Z_samples, Zs, slice * nsamples, cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess && keep && two && C_samples) e = cudaMemcpyAsync(C_samples, Cs, slice * nsamples, cudaMemcpyDeviceToHost, h->stream);
         if (e == cudaSuccess && Z_last) e = cudaMemcpyAsync(Z_last, h->Z, slice, cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess && two && C_last) e = cudaMemcpyAsync(C_last, Cd, slice, cudaMemcpyDeviceToHost, h->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
         float ms = 0; cudaEventElapsedTime(&ms, h->ev[0], h->ev[6]);
         h->timing.total_ms = ms; h->timing.iters = iter > 1 ? iter - 1 : 0;
     }
-    cudaFree(cF); cudaFree(cN); cudaFree(nw); cudaFree(Zs);
+    cudaFree(cF); cudaFree(cN); cudaFree(nw); cudaFree(Zs); cudaFree(cF2); cudaFree(cN2); cudaFree(Cd); cudaFree(Cs);
     if (e != cudaSuccess) { h->err = std::string("collapsed Gibbs: ") + cudaGetErrorString(e); cudaGetLastError(); return NBMF_ERR_CUDA; }
     if (rc) return rc;
     if (n_samples_written) *n_samples_written = written;
-    // the statistics of the handle follow the labels (checkpoint / hand-off to VB)
     return NBMF_OK;
+}
+
+extern "C" int nbmf_gibbs_dirber_collapsed(nbmf_handle *h, int K, double alpha, double beta, double gamma,
+                                           int iter, double burnin, uint64_t seed, int32_t *Z_samples,
+                                           int *n_samples_written, int32_t *Z_last)
+{
+    if (!h) return NBMF_ERR_ARG;
+    return collapsed_wavefront(h, 0, K, alpha, beta, gamma, iter, burnin, seed, Z_samples, nullptr, n_samples_written, Z_last, nullptr);
+}
+
+// Kmax = 200 components (collapsed_gibbs_z.cpp:282); alpha and beta are accepted and ignored, as in the
+// reference (its Beta prior is the constant epsilon = 1e-8, :281,317-318).  The labels must have been
+// installed with nbmf_init_from_labels(Z, 200).
+extern "C" int nbmf_gibbs_dirber_dp_collapsed(nbmf_handle *h, double alpha, double beta, double gamma, int iter,
+                                              double burnin, uint64_t seed, int32_t *Z_samples,
+                                              int *n_samples_written, int32_t *Z_last)
+{
+    if (!h) return NBMF_ERR_ARG;
+    (void)alpha; (void)beta;
+    if (h->Kc != 200) return fail(h, NBMF_ERR_STATE, "Gibbs_DirBer_DP_Rcpp works on Kmax = 200 components: call nbmf_init_from_labels(Z, 200)");
+    return collapsed_wavefront(h, 1, 200, 1.0, 1.0, gamma, iter, burnin, seed, Z_samples, nullptr, n_samples_written, Z_last, nullptr);
+}
+
+extern "C" int nbmf_gibbs_dirdir_collapsed(nbmf_handle *h, int K, double alpha, double gamma, int iter, double burnin,
+                                           uint64_t seed, int32_t *Z_samples, int32_t *C_samples,
+                                           int *n_samples_written, int32_t *Z_last, int32_t *C_last)
+{
+    if (!h) return NBMF_ERR_ARG;
+    return collapsed_wavefront(h, 2, K, alpha, 1.0, gamma, iter, burnin, seed, Z_samples, C_samples, n_samples_written, Z_last, C_last);
 }
 
 extern "C" int nbmf_gibbs_sweep_given_W(nbmf_handle *h, const int32_t *v_n, const double *W, int64_t F,

@@ -782,6 +782,145 @@ int oracle_gibbs_dirber_finite_keyed_wavefront(const int32_t *V, int32_t *Z, int
 }
 
 /* ------------------------------------------------------------------------ */
+/* Sibling collapsed samplers with the same keyed uniform. */
+/* ------------------------------------------------------------------------ */
+static double keyed_unif(uint64_t seed, int f, int n, int i, int second)
+{
+    uint32_t c[4] = {(uint32_t)f, (uint32_t)n, (uint32_t)i, 0u};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    uint64_t bits = second ? (((uint64_t)c[2] << 32) | c[3]) : (((uint64_t)c[0] << 32) | c[1]);
+    return ((double)(bits >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+}
+/* probs / accu(probs), then the inverse-CDF draw that stands in for rmultinom + index_max */
+static int normalise_and_draw(double *probs, int K, double u)
+{
+    double s = 0.0, acc = 0.0;
+    for (int k = 0; k < K; k++) s += probs[k];
+    for (int k = 0; k < K; k++) probs[k] /= s;
+    for (int k = 0; k < K; k++) { acc += probs[k]; if (u < acc) return k; }
+    for (int k = K - 1; k >= 0; k--) if (probs[k] > 0.0) return k;
+    return K - 1;
+}
+static void iremove(icounts *c, int f, int n, int k, int v)
+{   /* remove_assignment :75-85 */
+    c->f_ones[n + (size_t)c->N * k] -= v; c->f_zeros[n + (size_t)c->N * k] -= 1 - v;
+    c->f_total[n + (size_t)c->N * k] -= 1; c->n_total[f + (size_t)c->F * k] -= 1; c->fn_total[k] -= 1;
+}
+static void iset(icounts *c, int f, int n, int k, int v)
+{   /* set_assignment :63-72 */
+    c->f_ones[n + (size_t)c->N * k] += v; c->f_zeros[n + (size_t)c->N * k] += 1 - v;
+    c->f_total[n + (size_t)c->N * k] += 1; c->n_total[f + (size_t)c->F * k] += 1; c->fn_total[k] += 1;
+}
+
+/* Gibbs_DirBer_DP_Rcpp (collapsed_gibbs_z.cpp:275-359): Kmax = 200 components (:282), the
+ * Beta prior replaced by epsilon = 1e-8 on both counts (:281,317-318; alpha and beta are
+ * unused), weight n_total (no gamma) per occupied component (:321) and gamma/2 on the first
+ * empty one (:325-329).  The reference has no NA test (:308-310) and indexes probs[Kmax] when
+ * no component is empty: here V must be NA-free and a full row simply opens no new component. */
+static void dp_entry(const int32_t *V, int32_t *Z, icounts *cnt, double *probs, int F, int N, int K,
+                     double gamma, uint64_t seed, int i, int f, int n)
+{
+    const double epsilon = 0.00000001;
+    size_t e = (size_t)f + (size_t)F * n;
+    int v = V[e];
+    iremove(cnt, f, n, Z[e], v);
+    int k_free = -1;
+    for (int k = 0; k < K; k++) {
+        double ap = cnt->f_ones[n + (size_t)N * k] + epsilon;
+        double bp = cnt->f_zeros[n + (size_t)N * k] + epsilon;
+        double bpr = (v * ap + (1 - v) * bp) / (ap + bp);
+        probs[k] = cnt->n_total[f + (size_t)F * k] * bpr;
+        if (k_free < 0 && cnt->n_total[f + (size_t)F * k] == 0) k_free = k;
+    }
+    if (k_free >= 0) probs[k_free] = gamma * 0.5;
+    int k1 = normalise_and_draw(probs, K, keyed_unif(seed, f, n, i, 0));
+    Z[e] = k1;
+    iset(cnt, f, n, k1, v);
+}
+
+/* Gibbs_DirDir_finite_Rcpp (collapsed_gibbs_z.cpp:441-557): two assignments per entry.
+ * V = 1: Z and C drawn together from (gamma + n_total^Z_f) (alpha + f_total^C_n) (:481-497);
+ * V = 0: Z from gamma + n_total^Z_f with C's component forbidden (:500-512), then C from
+ * alpha + f_total^C_n with the new Z component forbidden (:514-531).                       */
+static void dirdir_entry(const int32_t *V, int32_t *Z, int32_t *C, icounts *cz, icounts *cc, double *probs,
+                         int F, int N, int K, double alpha, double gamma, uint64_t seed, int i, int f, int n)
+{
+    size_t e = (size_t)f + (size_t)F * n;
+    int v = V[e];
+    if (v == NA_INT) return;
+    if (v) {
+        iremove(cz, f, n, Z[e], v); iremove(cc, f, n, C[e], v);
+        for (int k = 0; k < K; k++)
+            probs[k] = (gamma + cz->n_total[f + (size_t)F * k]) * (alpha + cc->f_total[n + (size_t)N * k]);
+        int k = normalise_and_draw(probs, K, keyed_unif(seed, f, n, i, 0));
+        Z[e] = k; C[e] = k;
+        iset(cz, f, n, k, v); iset(cc, f, n, k, v);
+    } else {
+        iremove(cz, f, n, Z[e], v);
+        for (int k = 0; k < K; k++) probs[k] = gamma + cz->n_total[f + (size_t)F * k];
+        probs[C[e]] = 0;
+        int kz = normalise_and_draw(probs, K, keyed_unif(seed, f, n, i, 0));
+        iremove(cc, f, n, C[e], v);
+        for (int k = 0; k < K; k++) probs[k] = alpha + cc->f_total[n + (size_t)N * k];
+        probs[kz] = 0;
+        int kc = normalise_and_draw(probs, K, keyed_unif(seed, f, n, i, 1));
+        Z[e] = kz; C[e] = kc;
+        iset(cz, f, n, kz, v); iset(cc, f, n, kc, v);
+    }
+}
+
+/* variant 1 = DP (K is forced to 200, C ignored), 2 = Dir-Dir.  Same sweep bookkeeping as
+ * Gibbs_DirBer_finite_Rcpp; wavefront as in gibbs_keyed. */
+static int siblings_keyed(int variant, const int32_t *V, int32_t *Z, int32_t *C, int F, int N, int K, double alpha,
+                          double gamma, int iter, double burnin, uint64_t seed, int32_t *Z_samples,
+                          int32_t *C_samples, int wavefront)
+{
+    icounts cz, cc;
+    int nburnin = (int)floor(iter * burnin);
+    int nsamples = iter - (int)floor(iter * burnin);
+    int j = 0;
+    if (variant == 1) K = 200;
+    double *probs = malloc(sizeof(double) * K);
+    if (!probs || icounts_alloc(&cz, F, K, N) || icounts_alloc(&cc, F, K, N)) return -1;
+    if (Z_samples) memset(Z_samples, 0, 4 * (size_t)F * N * (nsamples > 0 ? nsamples : 0));
+    if (C_samples) memset(C_samples, 0, 4 * (size_t)F * N * (nsamples > 0 ? nsamples : 0));
+    compute_counts(V, Z, &cz);
+    if (variant == 2) { memcpy(C, Z, 4 * (size_t)F * N); compute_counts(V, C, &cc); } /* :465-473 */
+    for (int i = 1; i < iter; i++) {
+        for (int d = 0; d <= (wavefront ? F + N - 2 : N - 1); d++) {
+            int f_lo = wavefront ? (d - (N - 1) > 0 ? d - (N - 1) : 0) : 0;
+            int f_hi = wavefront ? (d < F - 1 ? d : F - 1) : F - 1;
+            for (int f = f_lo; f <= f_hi; f++) {
+                int n = wavefront ? d - f : d;
+                if (variant == 1) dp_entry(V, Z, &cz, probs, F, N, K, gamma, seed, i, f, n);
+                else dirdir_entry(V, Z, C, &cz, &cc, probs, F, N, K, alpha, gamma, seed, i, f, n);
+            }
+        }
+        if (i >= nburnin && j < nsamples) {
+            if (Z_samples) memcpy(Z_samples + (size_t)F * N * j, Z, 4 * (size_t)F * N);
+            if (C_samples) memcpy(C_samples + (size_t)F * N * j, C, 4 * (size_t)F * N);
+            j++;
+        }
+    }
+    free(probs); icounts_free(&cz); icounts_free(&cc);
+    return j;
+}
+
+int oracle_gibbs_dirber_dp_keyed(const int32_t *V, int32_t *Z, int F, int N, double gamma, int iter,
+                                 double burnin, uint64_t seed, int32_t *Z_samples, int wavefront)
+{
+    for (size_t e = 0; e < (size_t)F * N; e++) if (V[e] == NA_INT) return -2; /* undefined in the reference */
+    return siblings_keyed(1, V, Z, NULL, F, N, 200, 0.0, gamma, iter, burnin, seed, Z_samples, NULL, wavefront);
+}
+
+int oracle_gibbs_dirdir_keyed(const int32_t *V, int32_t *Z, int32_t *C, int F, int N, int K, double alpha,
+                              double gamma, int iter, double burnin, uint64_t seed, int32_t *Z_samples,
+                              int32_t *C_samples, int wavefront)
+{
+    return siblings_keyed(2, V, Z, C, F, N, K, alpha, gamma, iter, burnin, seed, Z_samples, C_samples, wavefront);
+}
+
+/* ------------------------------------------------------------------------ */
 /* expectation.GibbsDirBer  (R/generic_Gibbs_DirBer.R:54-101): per-sample    */
 /* E_W (Dirichlet mean) and E_H (Beta mean) from the counts of sample j,     */
 /* E_V = mean_j E_W E_H^T.  Also returns the across-sample means of E_W and  */

@@ -73,6 +73,12 @@ def lib():
         L.oracle_gibbs_dirber_finite_keyed.argtypes = L.oracle_gibbs_dirber_finite.argtypes
         L.oracle_gibbs_dirber_finite_keyed_wavefront.restype = C.c_int
         L.oracle_gibbs_dirber_finite_keyed_wavefront.argtypes = L.oracle_gibbs_dirber_finite.argtypes
+        L.oracle_gibbs_dirber_dp_keyed.restype = C.c_int
+        L.oracle_gibbs_dirber_dp_keyed.argtypes = [_ip, _ip, C.c_int, C.c_int, C.c_double, C.c_int, C.c_double,
+                                                   C.c_uint64, _ip, C.c_int]
+        L.oracle_gibbs_dirdir_keyed.restype = C.c_int
+        L.oracle_gibbs_dirdir_keyed.argtypes = [_ip, _ip, _ip, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double,
+                                                C.c_int, C.c_double, C.c_uint64, _ip, _ip, C.c_int]
         L.oracle_gibbs_expectation.restype = C.c_int
         L.oracle_gibbs_expectation.argtypes = [_ip, _ip, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
                                                C.c_double, C.c_double, _dp, _dp, _dp]
@@ -206,6 +212,34 @@ def gibbs_dirber_finite_keyed(V, Z, K, alpha=1.0, beta=1.0, gamma=1.0, iter=100,
                                                seed, _p(Zs, _ip))
     assert j >= 0
     return {"Z_samples": Zs[:, :, :ns], "written": j, "Z": Z}
+
+
+def gibbs_dirber_dp_keyed(V, Z, gamma=1.0, iter=100, burnin=0.5, seed=1, wavefront=False):
+    """Gibbs_DirBer_DP_Rcpp (collapsed_gibbs_z.cpp:275-359) with the keyed uniform; Kmax = 200, V NA-free."""
+    V = _i32(V); Z = _i32(Z).copy(order="F")
+    F, N = V.shape
+    ns = iter - int(np.floor(iter * burnin))
+    Zs = np.zeros((F, N, max(ns, 1)), dtype=np.int32, order="F")
+    j = lib().oracle_gibbs_dirber_dp_keyed(_p(V, _ip), _p(Z, _ip), F, N, gamma, iter, burnin, seed, _p(Zs, _ip),
+                                           int(wavefront))
+    if j == -2:
+        raise ValueError("Gibbs_DirBer_DP_Rcpp is undefined for V with NA (no NA test at :308-310)")
+    assert j >= 0
+    return {"Z_samples": Zs[:, :, :ns], "written": j, "Z": Z}
+
+
+def gibbs_dirdir_keyed(V, Z, K, alpha=1.0, gamma=1.0, iter=100, burnin=0.5, seed=1, wavefront=False):
+    """Gibbs_DirDir_finite_Rcpp (collapsed_gibbs_z.cpp:441-557) with the keyed uniforms."""
+    V = _i32(V); Z = _i32(Z).copy(order="F")
+    Cm = np.zeros_like(Z, order="F")
+    F, N = V.shape
+    ns = iter - int(np.floor(iter * burnin))
+    Zs = np.zeros((F, N, max(ns, 1)), dtype=np.int32, order="F")
+    Cs = np.zeros((F, N, max(ns, 1)), dtype=np.int32, order="F")
+    j = lib().oracle_gibbs_dirdir_keyed(_p(V, _ip), _p(Z, _ip), _p(Cm, _ip), F, N, K, alpha, gamma, iter, burnin, seed,
+                                        _p(Zs, _ip), _p(Cs, _ip), int(wavefront))
+    assert j >= 0
+    return {"Z_samples": Zs[:, :, :ns], "C_samples": Cs[:, :, :ns], "written": j, "Z": Z, "C": Cm}
 
 
 def gibbs_expectation(V, Z_samples, K, alpha, beta, gamma, want_EV=True):

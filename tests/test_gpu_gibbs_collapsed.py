@@ -69,3 +69,40 @@ def test_collapsed_needs_labels_and_rejects_bad_labels():
     e.init_from_labels(Z, 3)
     with pytest.raises(NbmfError):
         e.gibbs_dirber_collapsed(2, 1.0, 1.0, 1.0, 5, 0.5, 1)   # labels up to 2 with K = 2
+
+
+# ---------------------------------------------------------------------------
+# sibling samplers: DP and Dir-Dir, same bit-exact bar
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("F,N,iter,burnin", [(60, 90, 8, 0.5), (200, 300, 5, 0.4), (1100, 1150, 3, 0.5)])
+def test_dp_sampler_is_bit_exact(F, N, iter, burnin):
+    from nbmf_b200 import Gibbs_DirBer_DP_Rcpp
+    V, Z = _case(F, N, 3, 4, 0.0, 33)
+    ref = oracle.gibbs_dirber_dp_keyed(V, Z, 0.8, iter=iter, burnin=burnin, seed=17)
+    out = Gibbs_DirBer_DP_Rcpp(V, Z, 1.0, 1.0, 0.8, iter, burnin, seed=17)
+    assert out["written"] == ref["written"]
+    assert np.array_equal(out["Z_last"], ref["Z"]) and np.array_equal(out["Z_samples"], ref["Z_samples"])
+    assert out["Z_last"].max() >= 4        # new components were opened (the CRP term, :325-329)
+
+
+def test_dp_sampler_rejects_na():
+    from nbmf_b200 import Gibbs_DirBer_DP_Rcpp, NbmfError
+    V, Z = _case(30, 40, 2, 3, 0.2, 5)
+    with pytest.raises(NbmfError):
+        Gibbs_DirBer_DP_Rcpp(V, Z, 1.0, 1.0, 1.0, 4, 0.5)
+
+
+@pytest.mark.parametrize("F,N,K,na,iter,burnin", [(60, 90, 5, 0.1, 8, 0.25), (200, 300, 3, 0.0, 5, 0.5),
+                                                  (48, 70, 40, 0.1, 4, 0.5), (1100, 1150, 4, 0.05, 3, 0.5)])
+def test_dirdir_sampler_is_bit_exact(F, N, K, na, iter, burnin):
+    from nbmf_b200 import Gibbs_DirDir_finite_Rcpp
+    V, Z = _case(F, N, 3, K, na, 41)
+    ref = oracle.gibbs_dirdir_keyed(V, Z, K, 1.0, 0.7, iter=iter, burnin=burnin, seed=23)
+    out = Gibbs_DirDir_finite_Rcpp(V, Z, K, 1.0, 0.7, iter, burnin, seed=23)
+    obs = V != NA
+    assert out["written"] == ref["written"]
+    assert np.array_equal(out["Z_last"][obs], ref["Z"][obs]) and np.array_equal(out["C_last"][obs], ref["C"][obs])
+    assert np.array_equal(out["Z_samples"][obs], ref["Z_samples"][obs])
+    assert np.array_equal(out["C_samples"][obs], ref["C_samples"][obs])
+    ones = obs & (V == 1); zeros = obs & (V == 0)
+    assert np.array_equal(out["Z_last"][ones], out["C_last"][ones]) and np.all(out["Z_last"][zeros] != out["C_last"][zeros])

@@ -159,6 +159,30 @@ def test_keyed_collapsed_gibbs_is_order_independent(F, N, K, na):
     assert np.all((a["Z"][obs] >= 0) & (a["Z"][obs] < K))
 
 
+@pytest.mark.parametrize("F,N", [(17, 29), (40, 12)])
+def test_keyed_sibling_samplers_are_order_independent(F, N):
+    """DP (Kmax = 200, first empty component gets gamma/2) and Dir-Dir (two assignments per entry): the
+    column-major sweep and the anti-diagonal order give the same labels with keyed uniforms."""
+    V = make_problem(F, N, 3, 29)
+    Z = oracle.random_labels(V, 4, 3)
+    a = oracle.gibbs_dirber_dp_keyed(V, Z, 0.8, iter=8, burnin=0.5, seed=5)
+    b = oracle.gibbs_dirber_dp_keyed(V, Z, 0.8, iter=8, burnin=0.5, seed=5, wavefront=True)
+    assert a["written"] == b["written"] == 4 and np.array_equal(a["Z_samples"], b["Z_samples"])
+    assert a["Z"].min() >= 0 and a["Z"].max() < 200 and a["Z"].max() >= 4      # new components were opened
+    Vn = make_problem(F, N, 3, 31, 0.15)
+    Zn = oracle.random_labels(Vn, 5, 3)
+    c = oracle.gibbs_dirdir_keyed(Vn, Zn, 5, 1.0, 0.7, iter=8, burnin=0.25, seed=6)
+    d = oracle.gibbs_dirdir_keyed(Vn, Zn, 5, 1.0, 0.7, iter=8, burnin=0.25, seed=6, wavefront=True)
+    assert c["written"] == d["written"] == 6
+    assert np.array_equal(c["Z_samples"], d["Z_samples"]) and np.array_equal(c["C_samples"], d["C_samples"])
+    obs = Vn != NA
+    ones = obs & (Vn == 1); zeros = obs & (Vn == 0)
+    assert np.array_equal(c["Z"][ones], c["C"][ones])          # V = 1: drawn together (:481-497)
+    assert np.all(c["Z"][zeros] != c["C"][zeros])              # V = 0: the two components differ (:505,522)
+    with pytest.raises(ValueError):
+        oracle.gibbs_dirber_dp_keyed(Vn, Zn, 1.0, iter=3)
+
+
 def test_keyed_and_stream_collapsed_gibbs_sample_the_same_posterior():
     """The keyed uniforms replace the sequential stream, nothing else: the posterior mean of V (label
     invariant) of the two chains agrees within the seed-to-seed spread of either."""
