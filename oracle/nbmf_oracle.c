@@ -784,6 +784,13 @@ int oracle_gibbs_dirber_finite_keyed_wavefront(const int32_t *V, int32_t *Z, int
 /* ------------------------------------------------------------------------ */
 /* Sibling collapsed samplers with the same keyed uniform. */
 /* ------------------------------------------------------------------------ */
+/* stream != NULL: the next draw of the sequential stream (what the reference does with R's RNG and
+ * the reference build does with the shim's); else the counter-based one */
+static double keyed_unif(uint64_t seed, int f, int n, int i, int second);
+static double next_unif(orng *stream, uint64_t seed, int f, int n, int i, int second)
+{
+    return stream ? orng_unif(stream) : keyed_unif(seed, f, n, i, second);
+}
 static double keyed_unif(uint64_t seed, int f, int n, int i, int second)
 {
     uint32_t c[4] = {(uint32_t)f, (uint32_t)n, (uint32_t)i, 0u};
@@ -818,7 +825,7 @@ static void iset(icounts *c, int f, int n, int k, int v)
  * empty one (:325-329).  The reference has no NA test (:308-310) and indexes probs[Kmax] when
  * no component is empty: here V must be NA-free and a full row simply opens no new component. */
 static void dp_entry(const int32_t *V, int32_t *Z, icounts *cnt, double *probs, int F, int N, int K,
-                     double gamma, uint64_t seed, int i, int f, int n)
+                     double gamma, orng *stream, uint64_t seed, int i, int f, int n)
 {
     const double epsilon = 0.00000001;
     size_t e = (size_t)f + (size_t)F * n;
@@ -833,7 +840,7 @@ static void dp_entry(const int32_t *V, int32_t *Z, icounts *cnt, double *probs, 
         if (k_free < 0 && cnt->n_total[f + (size_t)F * k] == 0) k_free = k;
     }
     if (k_free >= 0) probs[k_free] = gamma * 0.5;
-    int k1 = normalise_and_draw(probs, K, keyed_unif(seed, f, n, i, 0));
+    int k1 = normalise_and_draw(probs, K, next_unif(stream, seed, f, n, i, 0));
     Z[e] = k1;
     iset(cnt, f, n, k1, v);
 }
@@ -843,7 +850,7 @@ static void dp_entry(const int32_t *V, int32_t *Z, icounts *cnt, double *probs, 
  * V = 0: Z from gamma + n_total^Z_f with C's component forbidden (:500-512), then C from
  * alpha + f_total^C_n with the new Z component forbidden (:514-531).                       */
 static void dirdir_entry(const int32_t *V, int32_t *Z, int32_t *C, icounts *cz, icounts *cc, double *probs,
-                         int F, int N, int K, double alpha, double gamma, uint64_t seed, int i, int f, int n)
+                         int F, int N, int K, double alpha, double gamma, orng *stream, uint64_t seed, int i, int f, int n)
 {
     size_t e = (size_t)f + (size_t)F * n;
     int v = V[e];
@@ -852,18 +859,18 @@ static void dirdir_entry(const int32_t *V, int32_t *Z, int32_t *C, icounts *cz, 
         iremove(cz, f, n, Z[e], v); iremove(cc, f, n, C[e], v);
         for (int k = 0; k < K; k++)
             probs[k] = (gamma + cz->n_total[f + (size_t)F * k]) * (alpha + cc->f_total[n + (size_t)N * k]);
-        int k = normalise_and_draw(probs, K, keyed_unif(seed, f, n, i, 0));
+        int k = normalise_and_draw(probs, K, next_unif(stream, seed, f, n, i, 0));
         Z[e] = k; C[e] = k;
         iset(cz, f, n, k, v); iset(cc, f, n, k, v);
     } else {
         iremove(cz, f, n, Z[e], v);
         for (int k = 0; k < K; k++) probs[k] = gamma + cz->n_total[f + (size_t)F * k];
         probs[C[e]] = 0;
-        int kz = normalise_and_draw(probs, K, keyed_unif(seed, f, n, i, 0));
+        int kz = normalise_and_draw(probs, K, next_unif(stream, seed, f, n, i, 0));
         iremove(cc, f, n, C[e], v);
         for (int k = 0; k < K; k++) probs[k] = alpha + cc->f_total[n + (size_t)N * k];
         probs[kz] = 0;
-        int kc = normalise_and_draw(probs, K, keyed_unif(seed, f, n, i, 1));
+        int kc = normalise_and_draw(probs, K, next_unif(stream, seed, f, n, i, 1));
         Z[e] = kz; C[e] = kc;
         iset(cz, f, n, kz, v); iset(cc, f, n, kc, v);
     }
@@ -873,9 +880,11 @@ static void dirdir_entry(const int32_t *V, int32_t *Z, int32_t *C, icounts *cz, 
  * Gibbs_DirBer_finite_Rcpp; wavefront as in gibbs_keyed. */
 static int siblings_keyed(int variant, const int32_t *V, int32_t *Z, int32_t *C, int F, int N, int K, double alpha,
                           double gamma, int iter, double burnin, uint64_t seed, int32_t *Z_samples,
-                          int32_t *C_samples, int wavefront)
+                          int32_t *C_samples, int wavefront, int use_stream)
 {
     icounts cz, cc;
+    orng g, *stream = use_stream ? &g : NULL;
+    if (use_stream) { orng_seed(&g, seed); wavefront = 0; }
     int nburnin = (int)floor(iter * burnin);
     int nsamples = iter - (int)floor(iter * burnin);
     int j = 0;
@@ -892,8 +901,8 @@ static int siblings_keyed(int variant, const int32_t *V, int32_t *Z, int32_t *C,
             int f_hi = wavefront ? (d < F - 1 ? d : F - 1) : F - 1;
             for (int f = f_lo; f <= f_hi; f++) {
                 int n = wavefront ? d - f : d;
-                if (variant == 1) dp_entry(V, Z, &cz, probs, F, N, K, gamma, seed, i, f, n);
-                else dirdir_entry(V, Z, C, &cz, &cc, probs, F, N, K, alpha, gamma, seed, i, f, n);
+                if (variant == 1) dp_entry(V, Z, &cz, probs, F, N, K, gamma, stream, seed, i, f, n);
+                else dirdir_entry(V, Z, C, &cz, &cc, probs, F, N, K, alpha, gamma, stream, seed, i, f, n);
             }
         }
         if (i >= nburnin && j < nsamples) {
@@ -906,18 +915,20 @@ static int siblings_keyed(int variant, const int32_t *V, int32_t *Z, int32_t *C,
     return j;
 }
 
+/* wavefront: 0 column-major / 1 anti-diagonal with keyed uniforms; 2 = column-major on the sequential
+ * stream (the form that is pinned against the reference's own sources, tests/test_oracle_pin.py) */
 int oracle_gibbs_dirber_dp_keyed(const int32_t *V, int32_t *Z, int F, int N, double gamma, int iter,
                                  double burnin, uint64_t seed, int32_t *Z_samples, int wavefront)
 {
     for (size_t e = 0; e < (size_t)F * N; e++) if (V[e] == NA_INT) return -2; /* undefined in the reference */
-    return siblings_keyed(1, V, Z, NULL, F, N, 200, 0.0, gamma, iter, burnin, seed, Z_samples, NULL, wavefront);
+    return siblings_keyed(1, V, Z, NULL, F, N, 200, 0.0, gamma, iter, burnin, seed, Z_samples, NULL, wavefront == 1, wavefront == 2);
 }
 
 int oracle_gibbs_dirdir_keyed(const int32_t *V, int32_t *Z, int32_t *C, int F, int N, int K, double alpha,
                               double gamma, int iter, double burnin, uint64_t seed, int32_t *Z_samples,
                               int32_t *C_samples, int wavefront)
 {
-    return siblings_keyed(2, V, Z, C, F, N, K, alpha, gamma, iter, burnin, seed, Z_samples, C_samples, wavefront);
+    return siblings_keyed(2, V, Z, C, F, N, K, alpha, gamma, iter, burnin, seed, Z_samples, C_samples, wavefront == 1, wavefront == 2);
 }
 
 /* ------------------------------------------------------------------------ */

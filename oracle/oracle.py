@@ -215,7 +215,8 @@ def gibbs_dirber_finite_keyed(V, Z, K, alpha=1.0, beta=1.0, gamma=1.0, iter=100,
 
 
 def gibbs_dirber_dp_keyed(V, Z, gamma=1.0, iter=100, burnin=0.5, seed=1, wavefront=False):
-    """Gibbs_DirBer_DP_Rcpp (collapsed_gibbs_z.cpp:275-359) with the keyed uniform; Kmax = 200, V NA-free."""
+    """Gibbs_DirBer_DP_Rcpp (collapsed_gibbs_z.cpp:275-359) with the keyed uniform; Kmax = 200, V NA-free.
+    `wavefront=2`: column-major on the sequential stream instead (the form pinned against the reference)."""
     V = _i32(V); Z = _i32(Z).copy(order="F")
     F, N = V.shape
     ns = iter - int(np.floor(iter * burnin))
@@ -229,7 +230,8 @@ def gibbs_dirber_dp_keyed(V, Z, gamma=1.0, iter=100, burnin=0.5, seed=1, wavefro
 
 
 def gibbs_dirdir_keyed(V, Z, K, alpha=1.0, gamma=1.0, iter=100, burnin=0.5, seed=1, wavefront=False):
-    """Gibbs_DirDir_finite_Rcpp (collapsed_gibbs_z.cpp:441-557) with the keyed uniforms."""
+    """Gibbs_DirDir_finite_Rcpp (collapsed_gibbs_z.cpp:441-557) with the keyed uniforms (`wavefront=2`: the
+    sequential stream, column-major)."""
     V = _i32(V); Z = _i32(Z).copy(order="F")
     Cm = np.zeros_like(Z, order="F")
     F, N = V.shape

@@ -35,6 +35,12 @@ def lib():
         L.ref_gibbs_dirber_finite.restype = C.c_int
         L.ref_gibbs_dirber_finite.argtypes = [_ip, _ip, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,
                                               C.c_int, C.c_double, C.c_uint64, _ip, _dp]
+        L.ref_gibbs_dirber_dp.restype = C.c_int
+        L.ref_gibbs_dirber_dp.argtypes = [_ip, _ip, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int,
+                                          C.c_double, C.c_uint64, _ip]
+        L.ref_gibbs_dirdir.restype = C.c_int
+        L.ref_gibbs_dirdir.argtypes = [_ip, _ip, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double,
+                                       C.c_uint64, _ip, _ip]
         L.ref_lower_bound_aspect.restype = C.c_double
         L.ref_lower_bound_aspect.argtypes = [_dp, _dp, _dp, _dp, _dp, _dp, _dp, C.c_double, C.c_double, C.c_double, _ip,
                                              C.c_int, C.c_int, C.c_int]
@@ -78,6 +84,28 @@ def gibbs_dirber_finite(V, Z, K, alpha=1.0, beta=1.0, gamma=1.0, iter=100, burni
                                       _p(Zs, _ip), None)
     assert n == ns, (n, ns)
     return {"Z_samples": Zs[:, :, :ns]}
+
+
+def gibbs_dirber_dp(V, Z, alpha=1.0, beta=1.0, gamma=1.0, iter=100, burnin=0.5, seed=1):
+    """Gibbs_DirBer_DP_Rcpp (src/collapsed_gibbs_z.cpp:275-359) on the shim RNG."""
+    V = _i32(V); Z = _i32(Z)
+    F, N = V.shape
+    ns = iter - int(np.floor(iter * burnin))
+    Zs = np.zeros((F, N, max(ns, 1)), dtype=np.int32, order="F")
+    n = lib().ref_gibbs_dirber_dp(_p(V, _ip), _p(Z, _ip), F, N, alpha, beta, gamma, iter, burnin, seed, _p(Zs, _ip))
+    assert n == ns, (n, ns)
+    return {"Z_samples": Zs[:, :, :ns]}
+
+
+def gibbs_dirdir(V, Z, K, alpha=1.0, gamma=1.0, iter=100, burnin=0.5, seed=1):
+    """Gibbs_DirDir_finite_Rcpp (src/collapsed_gibbs_z.cpp:441-557) on the shim RNG."""
+    V = _i32(V); Z = _i32(Z)
+    F, N = V.shape
+    ns = iter - int(np.floor(iter * burnin))
+    Zs = np.zeros((F, N, max(ns, 1)), dtype=np.int32, order="F"); Cs = np.zeros_like(Zs, order="F")
+    n = lib().ref_gibbs_dirdir(_p(V, _ip), _p(Z, _ip), F, N, K, alpha, gamma, iter, burnin, seed, _p(Zs, _ip), _p(Cs, _ip))
+    assert n == ns, (n, ns)
+    return {"Z_samples": Zs[:, :, :ns], "C_samples": Cs[:, :, :ns]}
 
 
 def compute_expectations(Z_samples, V, alpha, beta, gamma):

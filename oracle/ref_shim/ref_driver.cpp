@@ -6,6 +6,8 @@
 SEXP VB_Aspect_Rcpp(const arma::imat &V, arma::imat Z, int K, double alpha, double beta, double gamma, int iter, bool checklb);
 SEXP VB_DirBer_Rcpp(const arma::imat &V, arma::imat Z, int K, double alpha, double beta, double gamma, int iter);
 SEXP Gibbs_DirBer_finite_Rcpp(const arma::imat &V, arma::imat Z, int K, double alpha, double beta, double gamma, int iter, double burnin);
+SEXP Gibbs_DirBer_DP_Rcpp(const arma::imat &V, arma::imat Z, double alpha, double beta, double gamma, int iter, double burnin);
+SEXP Gibbs_DirDir_finite_Rcpp(const arma::imat &V, arma::imat Z, int K, double alpha, double gamma, int iter, double burnin);
 double lower_bound_aspect(const arma::cube &E_Z, const arma::mat &E_log_W, const arma::mat &E_log_H, const arma::mat &E_log_1_H,
                           const arma::mat &gamma_vb, const arma::mat &alpha_vb, const arma::mat &beta_vb, double alpha, double beta,
                           double gamma, const arma::imat &V);
@@ -58,6 +60,35 @@ int ref_gibbs_dirber_finite(const int *V, const int *Z, int F, int N, int K, dou
         int ns = zs->dim.size() == 3 ? (int)zs->dim[2] : 0;
         if (Z_samples) std::copy(zs->integer.begin(), zs->integer.end(), Z_samples);
         copy_real(r, "E_Z", E_Z);
+        delete r;
+        return ns;
+    } catch (const std::exception &) { return -1; }
+}
+
+// the sibling samplers (collapsed_gibbs_z.cpp:275-359, :441-557); sample cubes F x N x nsamples
+int ref_gibbs_dirber_dp(const int *V, const int *Z, int F, int N, double alpha, double beta, double gamma, int iter, double burnin,
+                        unsigned long long seed, int *Z_samples)
+{
+    try {
+        shim::rng().seed(seed);
+        SEXP r = Gibbs_DirBer_DP_Rcpp(to_imat(V, F, N), to_imat(Z, F, N), alpha, beta, gamma, iter, burnin);
+        shim::Obj *zs = r->get("Z_samples");
+        int ns = zs->dim.size() == 3 ? (int)zs->dim[2] : 0;
+        if (Z_samples) std::copy(zs->integer.begin(), zs->integer.end(), Z_samples);
+        delete r;
+        return ns;
+    } catch (const std::exception &) { return -1; }
+}
+int ref_gibbs_dirdir(const int *V, const int *Z, int F, int N, int K, double alpha, double gamma, int iter, double burnin,
+                     unsigned long long seed, int *Z_samples, int *C_samples)
+{
+    try {
+        shim::rng().seed(seed);
+        SEXP r = Gibbs_DirDir_finite_Rcpp(to_imat(V, F, N), to_imat(Z, F, N), K, alpha, gamma, iter, burnin);
+        shim::Obj *zs = r->get("Z_samples"), *cs = r->get("C_samples");
+        int ns = zs->dim.size() == 3 ? (int)zs->dim[2] : 0;
+        if (Z_samples) std::copy(zs->integer.begin(), zs->integer.end(), Z_samples);
+        if (C_samples) std::copy(cs->integer.begin(), cs->integer.end(), C_samples);
         delete r;
         return ns;
     } catch (const std::exception &) { return -1; }

@@ -43,5 +43,11 @@ for name, (F, N, K, na, al, be, ga, it) in cases.items():
     out[f"gibbs_{name}_Z_samples"] = g["Z_samples"]
     ew, eh = ref.compute_expectations(g["Z_samples"], V, al, be, ga)
     out[f"gibbs_{name}_E_W"] = ew; out[f"gibbs_{name}_E_H"] = eh
+    # sibling samplers (collapsed_gibbs_z.cpp:441-557, :275-359; the DP one is undefined with NA)
+    dd = ref.gibbs_dirdir(V, Z, K, al, ga, iter=13, burnin=0.5, seed=9)
+    out[f"dirdir_{name}_Z_samples"] = dd["Z_samples"]; out[f"dirdir_{name}_C_samples"] = dd["C_samples"]
+    if na == 0.0:
+        dp = ref.gibbs_dirber_dp(V, Z, al, be, ga, iter=13, burnin=0.5, seed=9)
+        out[f"dp_{name}_Z_samples"] = dp["Z_samples"]
 np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_vectors.npz"), **out)
 print("wrote", len(out), "arrays")

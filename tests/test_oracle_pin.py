@@ -56,6 +56,22 @@ def test_gibbs_matches_reference_golden_draw_for_draw(c):
     assert np.allclose(EH, G[f"gibbs_{c}_E_H"], rtol=1e-13, atol=0)
 
 
+@pytest.mark.parametrize("c", CASES)
+def test_sibling_samplers_match_reference_golden_draw_for_draw(c):
+    """Gibbs_DirDir_finite_Rcpp (:441-557) and Gibbs_DirBer_DP_Rcpp (:275-359) on the sequential stream: the
+    oracle's restatements reproduce the sample cubes of the reference's own code.  The keyed forms the engine
+    is tested against share every line with these except the source of the uniform."""
+    K, al, be, ga, _ = G[f"aspect_{c}_par"]
+    V = G[f"aspect_{c}_V"]; Z = G[f"aspect_{c}_Z"]
+    obs = V != oracle.NA
+    d = oracle.gibbs_dirdir_keyed(V, Z, int(K), al, ga, iter=13, burnin=0.5, seed=9, wavefront=2)
+    assert np.array_equal(d["Z_samples"][obs], G[f"dirdir_{c}_Z_samples"][obs])
+    assert np.array_equal(d["C_samples"][obs], G[f"dirdir_{c}_C_samples"][obs])
+    if f"dp_{c}_Z_samples" in G:
+        p = oracle.gibbs_dirber_dp_keyed(V, Z, ga, iter=13, burnin=0.5, seed=9, wavefront=2)
+        assert np.array_equal(p["Z_samples"], G[f"dp_{c}_Z_samples"])
+
+
 @pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built (needs /root/reference)")
 def test_live_reference_build_equals_oracle():
     V, _, _ = oracle.generate(37, 29, 3, 0.4, 0.4, 99)
@@ -76,6 +92,16 @@ def test_live_reference_build_equals_oracle():
     assert np.array_equal(g["Z_samples"], h["Z_samples"])
     # lower_bound_aspect of the reference on the reference's own E_Z == the trace value
     assert not b["stopped"]
+    # sibling samplers on the sequential stream
+    obs = V != oracle.NA
+    d = oracle.gibbs_dirdir_keyed(V, Z, K, 1.2, 0.4, iter=15, burnin=0.3, seed=5, wavefront=2)
+    r = ref.gibbs_dirdir(V, Z, K, 1.2, 0.4, iter=15, burnin=0.3, seed=5)
+    assert np.array_equal(d["Z_samples"][obs], r["Z_samples"][obs]) and np.array_equal(d["C_samples"][obs], r["C_samples"][obs])
+    Vf, _, _ = oracle.generate(31, 23, 3, 0.4, 0.4, 5)
+    Zf = oracle.random_labels(Vf, 6, 8)
+    p = oracle.gibbs_dirber_dp_keyed(Vf, Zf, 1.7, iter=15, burnin=0.3, seed=5, wavefront=2)
+    q = ref.gibbs_dirber_dp(Vf, Zf, 1.0, 1.0, 1.7, iter=15, burnin=0.3, seed=5)
+    assert np.array_equal(p["Z_samples"], q["Z_samples"]) and p["Z_samples"].max() >= 6
 
 
 @pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built (needs /root/reference)")
