@@ -96,7 +96,7 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_run(wl, steps, warmup, sample_F=1024, sample_N=1024):
+def cpu_reference_run(wl, steps, warmup, sample_F=768, sample_N=1024):
     """The reference's CPU path (oracle/_ref if built, else the oracle port), 1 thread
     (the reference is single-threaded), on a bounded sample of the workload."""
     from oracle import oracle
@@ -105,7 +105,8 @@ def cpu_reference_run(wl, steps, warmup, sample_F=1024, sample_N=1024):
     V, _, _ = oracle.generate(F, N, wl["Kt"], wl["a"], wl["b"], wl["seed"])
     Z = oracle.random_labels(V, K, wl["seed"] + 1)
     kind = "port"
-    fn = lambda it: oracle.vb_aspect(V, Z, K, 1.0, 1.0, wl["gamma"], iter=it, checklb=False)
+    # checklb=True: the ELBO is evaluated every iteration, as in the GPU arm's timed step
+    fn = lambda it: oracle.vb_aspect(V, Z, K, 1.0, 1.0, wl["gamma"], iter=it, checklb=True)
     # the oracle call includes the one-hot E_Z init (as the reference does); time a
     # warmup-iteration call and a (warmup+steps)-iteration call and take the difference
     t0 = time.perf_counter(); fn(max(warmup, 1)); t1 = time.perf_counter()
@@ -117,14 +118,14 @@ def cpu_reference_run(wl, steps, warmup, sample_F=1024, sample_N=1024):
         # containers make it slower than real Armadillo would be, so it is reported, not used as `value`
         from oracle import ref as oref
         if oref.available() and F * N * K <= 1 << 25:
-            t3 = time.perf_counter(); oref.vb_aspect(V, Z, K, 1.0, 1.0, wl["gamma"], iter=1); t4 = time.perf_counter()
-            oref.vb_aspect(V, Z, K, 1.0, 1.0, wl["gamma"], iter=3); t5 = time.perf_counter()
+            t3 = time.perf_counter(); oref.vb_aspect(V, Z, K, 1.0, 1.0, wl["gamma"], iter=1, checklb=True); t4 = time.perf_counter()
+            oref.vb_aspect(V, Z, K, 1.0, 1.0, wl["gamma"], iter=3, checklb=True); t5 = time.perf_counter()
             extra["ref_shim_build_value"] = F * N * K * 2 / max((t5 - t4) - (t4 - t3), 1e-9)
     except Exception:
         pass
     return dict(value=val, unit=UNIT, cores=1, kind=kind,
                 sample=f"{F}x{N} synthetic DirBer (same generator), K={K}, {steps} sequential VB_Aspect_Rcpp "
-                       f"iterations (oracle port, bit-identical to the reference sources compiled against "
+                       f"iterations with checklb=TRUE (oracle port, bit-identical to the reference sources compiled against "
                        f"oracle/ref_shim), 1 thread (the reference has no threading); host has {os.cpu_count()} cores",
                 **extra), dt
 
@@ -138,7 +139,8 @@ def run_reference(args, wl):
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": steps, "warmup": min(args.warmup, 2), "ms_per_step": 1e3 * dt / steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": {"workload": wl["desc"], "F": wl["F"], "N": wl["N"], "K": wl["K"]},
+            "data": "synthetic", "config": {"workload": wl["desc"], "F": wl["F"], "N": wl["N"], "K": wl["K"],
+                                            "step": "one VB_aspect iteration: parameters, both statistics, ELBO (checklb=TRUE)"},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -193,7 +195,7 @@ def main():
 
     eng.vb_begin(K, 1.0, 1.0, wl["gamma"])
     for _ in range(max(args.warmup, 3)):
-        eng.vb_step(False)
+        eng.vb_step(True)
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
@@ -203,7 +205,7 @@ def main():
     barrier()
     e0.record(ext)
     for _ in range(args.steps):
-        eng.vb_step(False)
+        eng.vb_step(True)      # the full iteration of the north star: both statistics AND the ELBO
     e1.record(ext)
     barrier()
     ms = e0.elapsed_time(e1)
@@ -279,6 +281,7 @@ def main():
                           2: "f16 (hi only; validated at this size, profiles/r1_error_growth_c5.log) / f32 accumulate in TMEM"}[int(tim["path"])],
                 "data": "synthetic",
                 "config": {"workload": wl["desc"], "F": F, "N": N, "K": K, "columns_per_rank": Nl,
+                           "step": "one VB_aspect iteration: parameters, both statistics, ELBO (checklb=TRUE)",
                            "l2_policy": "inputs larger than L2 (bit planes + operands stream from HBM)"
                            if F * N / 8 > 126e6 else "inputs smaller than L2; no flush (latency-sized config)"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof}
