@@ -454,6 +454,73 @@ def Gibbs_DirBer(V, Z, K, alpha=1.0, beta=1.0, gamma=1.0, iter=100, burnin=0.5, 
     return res
 
 
+# -- host-side mirrors of the posterior-mean helpers the R wrappers apply to the sample cubes ----------
+# (compute_expectation_W_Rcpp :178-197, compute_expectation_H_Rcpp :230-272,
+#  compute_expectation_H_dirdir_Rcpp :205-225; O(F N J) integer reductions on cubes that are already on
+#  the host -- post-processing, not the hot path)
+def compute_expectation_W_Rcpp(Z_samples, gamma):
+    """normalise(gamma + mean_j n_total_j) over max(label)+1 columns; NA labels count for nothing."""
+    Zs = np.asarray(Z_samples)
+    F, N, J = Zs.shape
+    K = int(Zs.max()) + 1
+    E = np.empty((F, K), order="F")
+    for k in range(K):
+        E[:, k] = gamma + (Zs == k).sum(axis=(1, 2)) / J
+    return np.asfortranarray(E / E.sum(axis=1, keepdims=True))
+
+
+def compute_expectation_H_Rcpp(Z_samples, V, alpha, beta):
+    """mean_j (alpha + ones_j) / (alpha + beta + total_j); the reference's k loop stops at max(label), so
+    the last column stays zero (:236-242) -- kept."""
+    Zs = np.asarray(Z_samples); Vi = as_imat(V)
+    F, N, J = Zs.shape
+    K = int(Zs.max()) + 1
+    obs = (Vi != NA_INTEGER)[:, :, None]
+    one = (Vi == 1)[:, :, None]
+    E = np.zeros((N, K), order="F")
+    for k in range(K - 1):
+        m = (Zs == k) & obs
+        ones = (m & one).sum(axis=0); tot = m.sum(axis=0)          # N x J
+        E[:, k] = ((alpha + ones) / (alpha + beta + tot)).mean(axis=1)
+    return E
+
+
+def compute_expectation_H_dirdir_Rcpp(C_samples, alpha):
+    """normalise(alpha + mean_j column counts of C) (generic_Gibbs_DirDir.R:40-43)."""
+    Cs = np.asarray(C_samples)
+    F, N, J = Cs.shape
+    K = int(Cs.max()) + 1
+    E = np.empty((N, K), order="F")
+    for k in range(K):
+        E[:, k] = alpha + (Cs == k).sum(axis=(0, 2)) / J
+    return np.asfortranarray(E / E.sum(axis=1, keepdims=True))
+
+
+def Gibbs_DirBer_DP(V, Z, alpha=1.0, beta=1.0, gamma=1.0, iter=100, burnin=0.5, **kw):
+    """R/generic_Gibbs_DirBer_DP.R:1-28."""
+    res = Gibbs_DirBer_DP_Rcpp(V, _zero_base(Z), alpha, beta, gamma, iter, burnin, **kw)
+    res["E_W"] = compute_expectation_W_Rcpp(res["Z_samples"], gamma)
+    res["E_H"] = compute_expectation_H_Rcpp(res["Z_samples"], V, alpha, beta)
+    _check_nonneg(res)
+    res.update(alpha=alpha, beta=beta, gamma=gamma)
+    res["class"] = ("GibbsDirBer", "Bernoulli")
+    return res
+
+
+def Gibbs_DirDir(V, Z, K, alpha=1.0, gamma=1.0, iter=100, burnin=0.5, **kw):
+    """R/generic_Gibbs_DirDir.R:1-34."""
+    res = Gibbs_DirDir_finite_Rcpp(V, _zero_base(Z), K, alpha, gamma, iter, burnin, **kw)
+    res["E_W"] = compute_expectation_W_Rcpp(res["Z_samples"], gamma)
+    res["E_H"] = compute_expectation_H_dirdir_Rcpp(res["C_samples"], alpha)
+    _check_nonneg(res)
+    Vi = as_imat(V)
+    if res["E_W"].shape[0] != Vi.shape[0] or res["E_H"].shape[0] != Vi.shape[1]:
+        raise ValueError("Dimensions E_H and V do not match")
+    res.update(V=Vi, alpha=alpha, gamma=gamma)
+    res["class"] = ("GibbsDirDir", "Bernoulli")
+    return res
+
+
 def expectation(model):
     """R/commons.R:31-33 (VB) -- E_W %*% t(E_H).  For Gibbs results the engine
     already accumulated mean_j E_W^(j) E_H^(j)T on the held-out entries."""
@@ -473,8 +540,7 @@ def loglikelihood(model, V_test, *, device=0):
 
 def BernoulliNMF(V, K, K_init=None, model="DirBer", method="Gibbs", alpha=1.0, beta=1.0, gamma=1.0,
                  iter=1000, burnin=0.5, Z_init=None, *, seed=0, device=0):
-    """R/BernoulliNMF.R:12-106 for the models on the hot path (VB: aspectRcpp,
-    DirBer; Gibbs: DirBer).  Z initialisation: uniform labels on observed entries
+    """R/BernoulliNMF.R:12-106 (VB: aspectRcpp, DirBer; Gibbs: DirBer, DirBerDP, DirDir).  Z initialisation: uniform labels on observed entries
     (:23-33); Gibbs warm-starts with 100 VB iterations at K_init=10 and takes the
     arg-max of E_Z (:41-52) -- computed on the device from the final operands."""
     Vi = as_imat(V)
@@ -492,24 +558,30 @@ def BernoulliNMF(V, K, K_init=None, model="DirBer", method="Gibbs", alpha=1.0, b
         if Z.shape != Vi.shape:
             raise ValueError("dim(Z) != dim(V)")
     if method == "Gibbs":
-        if model != "DirBer":
-            raise NotImplementedError("only model='DirBer' is on the accelerated path")
-        if K < 10:
+        if model not in ("DirBer", "DirBerDP", "DirDir"):
+            raise ValueError("model must be 'DirBer', 'DirBerDP' or 'DirDir' for method='Gibbs'")
+        if model != "DirBerDP" and K < 10:
             raise ValueError("K < K_init=10: the reference would write counters out of bounds "
                              "(BernoulliNMF.R:18-20, SURVEY.md Appendix B.9)")
         # warm start and which.max hand-off on the device: no E_Z cube crosses the boundary
-        e = Engine(device=device)
+        e = Engine(device=device, precision=_lib.PREC_FP64 if model != "DirBer" else _lib.PREC_AUTO)
         try:
             e.set_data(Vi)
             e.init_from_labels(_zero_base(Z), K_init)
             e.vb_aspect(K_init, alpha, beta, gamma, iter=100)
-            e.argmax_labels()
-            E_W, E_H, E_V, Zl = e.gibbs_dirber(K, alpha, beta, gamma, iter, burnin, seed, None, want_Z=True)
+            Zw = e.argmax_labels(want_host=(model != "DirBer"))
+            if model == "DirBer":
+                E_W, E_H, E_V, Zl = e.gibbs_dirber(K, alpha, beta, gamma, iter, burnin, seed, None, want_Z=True)
         finally:
             e.close()
-        res = {"E_W": E_W, "E_H": E_H, "E_V_test": E_V, "Z_last": Zl, "V": Vi, "alpha": alpha, "beta": beta,
-               "gamma": gamma, "class": ("GibbsDirBer", "Bernoulli")}
-        _check_nonneg(res)
+        if model == "DirBer":
+            res = {"E_W": E_W, "E_H": E_H, "E_V_test": E_V, "Z_last": Zl, "V": Vi, "alpha": alpha, "beta": beta,
+                   "gamma": gamma, "class": ("GibbsDirBer", "Bernoulli")}
+            _check_nonneg(res)
+        elif model == "DirBerDP":       # BernoulliNMF.R:60-64
+            res = Gibbs_DirBer_DP(Vi, Zw, alpha, beta, gamma, iter, burnin, seed=seed, device=device)
+        else:                           # BernoulliNMF.R:66-70
+            res = Gibbs_DirDir(Vi, Zw, K, alpha, gamma, iter, burnin, seed=seed, device=device)
     elif method == "VB":
         if model == "aspectRcpp" or model == "aspect":
             res = VB_aspectRcpp(Vi, Z, K, alpha, beta, gamma, iter, device=device)

@@ -106,3 +106,20 @@ def test_dirdir_sampler_is_bit_exact(F, N, K, na, iter, burnin):
     assert np.array_equal(out["C_samples"][obs], ref["C_samples"][obs])
     ones = obs & (V == 1); zeros = obs & (V == 0)
     assert np.array_equal(out["Z_last"][ones], out["C_last"][ones]) and np.all(out["Z_last"][zeros] != out["C_last"][zeros])
+
+
+def test_bernoulli_nmf_model_matrix():
+    """BernoulliNMF(method="Gibbs", model=...) (BernoulliNMF.R:41-71): VB warm start at K_init = 10, which.max
+    hand-off, then the sampler of the model; the R wrappers' posterior means on the sample cubes."""
+    from nbmf_b200 import BernoulliNMF
+    V, _, _ = oracle.generate(40, 60, 3, 0.4, 0.4, 9)
+    V = np.asfortranarray(V)
+    r = BernoulliNMF(V, 12, model="DirDir", method="Gibbs", iter=12, burnin=0.5, seed=4)
+    assert r["class"] == ("GibbsDirDir", "Bernoulli") and r["E_W"].shape[0] == 40 and r["E_H"].shape[0] == 60
+    assert np.allclose(r["E_W"].sum(1), 1.0) and np.allclose(r["E_H"].sum(1), 1.0) and r["Z_samples"].shape == (40, 60, 6)
+    p = BernoulliNMF(V, 12, model="DirBerDP", method="Gibbs", iter=12, burnin=0.5, gamma=0.5, seed=4)
+    assert p["class"] == ("GibbsDirBer", "Bernoulli") and p["Z_samples"].shape == (40, 60, 6)
+    assert np.allclose(p["E_W"].sum(1), 1.0) and np.all((p["E_H"] >= 0) & (p["E_H"] <= 1))
+    # the same call twice is the same chain
+    p2 = BernoulliNMF(V, 12, model="DirBerDP", method="Gibbs", iter=12, burnin=0.5, gamma=0.5, seed=4)
+    assert np.array_equal(p2["Z_samples"], p["Z_samples"])
