@@ -58,3 +58,17 @@ def test_product_package_never_uses_oracle():
             txt = open(os.path.join(dirpath, fn), errors="ignore").read()
             assert "import oracle" not in txt and "from oracle" not in txt, fn
             assert "oracle/" not in txt and "nbmf_oracle" not in txt and "libnbmf_ref" not in txt, fn
+
+
+def test_glue_sources_use_only_declared_entry_points():
+    """integration/nbmf_glue.cpp (the bodies for the reference's Rcpp functions) and the snippets of
+    INTEGRATION.md call nothing but what include/nbmf_cuda.h declares."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    declared = set(re.findall(r"\b(nbmf_[a-z0-9_]+)\s*\(", open(os.path.join(root, "include", "nbmf_cuda.h")).read()))
+    types = {"nbmf_handle", "nbmf_opts", "nbmf_timing", "nbmf_allreduce_fn", "nbmf_precision", "nbmf_dirber_mode"}
+    for rel in ("integration/nbmf_glue.cpp", "integration/nbmf_glue.h", "INTEGRATION.md"):
+        text = open(os.path.join(root, rel)).read()
+        used = set(re.findall(r"\b(nbmf_[a-z0-9_]+)\s*\(", text)) - types
+        used = {u for u in used if not u.startswith("nbmf_glue") and not u.startswith("nbmf_b200")}
+        assert used <= declared, (rel, sorted(used - declared))
