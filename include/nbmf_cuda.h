@@ -45,14 +45,29 @@ typedef enum nbmf_status {
 
 /* which arithmetic the contraction kernel uses */
 typedef enum nbmf_precision {
-    NBMF_PREC_AUTO = 0,        /* FP64 FMA path for K <= 32 or small F,N; tensor path otherwise,
-                                  hi-only stage 2 once min(F, N) >= 131072  */
-    NBMF_PREC_FP64 = 1,        /* FP64 FMA + warp shuffles (any K <= 512)                 */
+    NBMF_PREC_AUTO = 0,        /* the fastest variant whose measured error growth stays inside the
+                                  1e-5 gate on W and H for the planned number of iterations at
+                                  this size (nbmf_opts.planned_iters):
+                                  FP64 for K <= 32 or small F, N, else one of the tensor variants */
+    NBMF_PREC_FP64 = 1,        /* FP64: DMMA tensor pipe for Kp <= 128, FMA + shuffles above       */
     NBMF_PREC_TENSOR = 2,      /* tcgen05 f16: stage 2 with the streamed operand split hi+lo,
-                                  fp32 accumulate in TMEM (1e-5 parity at every size tested) */
-    NBMF_PREC_TENSOR_FAST = 3  /* same, hi only in stage 2: 1/3 fewer MMAs; its error falls
-                                  like ~1/sqrt(min(F,N)) -- see DESIGN.md before using it   */
+                                  fp32 accumulate in TMEM                                          */
+    NBMF_PREC_TENSOR_FAST = 3, /* same, hi only in stage 2: 1/3 fewer MMAs; its error falls
+                                  like ~1/sqrt(min(F,N)) -- short runs at very large sizes         */
+    NBMF_PREC_TENSOR_ACC = 4,  /* hi+lo in stage 2 AND the owner operand's lo part in stage 1: removes
+                                  the one error that does not average out over the reduction;
+                                  4/2 of the FAST variant's MMAs                                   */
+    NBMF_PREC_FP32 = 5         /* FP32 FMA + warp shuffles (small K, short runs)    */
 } nbmf_precision;
+
+/* contraction actually used by the last VB session (nbmf_timing.path) */
+typedef enum nbmf_path {
+    NBMF_PATH_FP64 = 0,
+    NBMF_PATH_TENSOR = 1,      /* f16, stage 2 hi+lo          */
+    NBMF_PATH_TENSOR_FAST = 2, /* f16, hi only                */
+    NBMF_PATH_TENSOR_ACC = 3,  /* f16, stage 1 and 2 hi+lo    */
+    NBMF_PATH_FP32 = 4
+} nbmf_path;
 
 /* VB_DirBer_Rcpp modes */
 typedef enum nbmf_dirber_mode {
@@ -67,6 +82,11 @@ typedef struct nbmf_opts {
     int pipe_block_cols; /* nbmf_vb_aspect_bits: columns per upload block; 0 = about N/8         */
     int64_t n_global;    /* column sharding: total number of columns (0 = not sharded)      */
     int64_t n_offset;    /* first global column this handle owns                            */
+    int planned_iters;   /* AUTO precision: VB updates the caller will run from this start
+                            (nbmf_vb_begin / nbmf_vb_step sessions; nbmf_vb_aspect* use their own
+                            iter).  0 = unknown = 100, VB_Aspect_Rcpp's default
+                            (collapsed_gibbs_z_VB.cpp:376)                                   */
+    int reserved;
 } nbmf_opts;
 
 typedef struct nbmf_handle nbmf_handle;
@@ -89,7 +109,7 @@ typedef struct nbmf_timing {
     double exchange_ms;
     int64_t launches;       /* kernels launched inside the loop              */
     int64_t iters;
-    int64_t path;           /* contraction used: 0 FP64 FMA, 1 tensor (hi+lo stage 2), 2 tensor (hi only) */
+    int64_t path;           /* nbmf_path of the session */
 } nbmf_timing;
 
 const char *nbmf_version(void);
@@ -149,7 +169,11 @@ int nbmf_vb_aspect(nbmf_handle *h, int K, double alpha, double beta, double gamm
  * the column-packed bit plane of nbmf_set_data_bits (no NA), n_total / f_ones / f_zeros the
  * vbcounts of nbmf_set_stats.  The upload is cut into column blocks and the first iteration
  * consumes them as they arrive, so the host->device transfer overlaps the contraction; pinned
- * host memory is needed for that overlap (pageable memory still works, serially).        */
+ * host memory is needed for that overlap (pageable memory still works, serially).  E_W and
+ * E_H are the parameters at the top of the last iteration (:507-514), so they start their
+ * way back beside that iteration.  With a communicator (nbmf_comm_init_rank, or inside a
+ * group) the row-side arrays belong to rank 0: n_total is read there and broadcast over
+ * NVLink (other ranks may pass NULL), and E_W may be NULL on the other ranks.            */
 int nbmf_vb_aspect_bits(nbmf_handle *h, const uint32_t *vbits, int64_t F, int64_t N, int K,
                         double alpha, double beta, double gamma, int iter, int checklb,
                         const double *n_total, const double *f_ones, const double *f_zeros,
@@ -239,6 +263,98 @@ int nbmf_gibbs_sweep_given_W(nbmf_handle *h, const int32_t *v_n, const double *W
 int nbmf_predictive_ll(nbmf_handle *h, const double *E_W, const double *E_H, int K,
                        const int32_t *V_test_colmajor, int64_t F, int64_t N, double *ll,
                        int64_t *n_test);
+
+/* ---- posterior-mean reducers of the collapsed samplers ------------------------
+ * compute_expectation_W_Rcpp (collapsed_gibbs_z.cpp:178-197) and
+ * compute_expectation_H_Rcpp (:230-272) on the device.  Z_samples: F x N x J int32
+ * (arma::icube layout), NA = INT_MIN; Kq = max label + 1 (the reference sizes its
+ * outputs by Z_samples.max(), :180,236); E_W F x Kq, E_H N x Kq with the last column
+ * left at 0 as the reference's k < K loop leaves it (:236-242).  Bit-identical to the
+ * reference (same order of the sum over samples).                                  */
+int nbmf_compute_expectation_W(nbmf_handle *h, const int32_t *Z_samples, int64_t F, int64_t N, int J,
+                               double gamma, int Kq, double *E_W);
+int nbmf_compute_expectation_H(nbmf_handle *h, const int32_t *Z_samples, const int32_t *V_colmajor,
+                               int64_t F, int64_t N, int J, double alpha, double beta, int Kq,
+                               double *E_H);
+
+/* ---- samples_VWH_DirBer (collapsed_gibbs_z.cpp:565-625) ------------------------
+ * for every kept label matrix: W_f ~ Dir(gamma + n_total_f) (normalised Gammas),
+ * H_nk ~ Beta(alpha + ones, beta + zeros), V ~ Bernoulli(W H^T); R's stream is
+ * replaced by Philox keyed (seed; sample, row / column, component).  K = max label + 1
+ * (:573).  W_samples F x K x J, H_samples N x K x J, V_samples F x N x J; any may be
+ * NULL.                                                                            */
+int nbmf_samples_VWH_DirBer(nbmf_handle *h, const int32_t *V_colmajor, const int32_t *Z_samples,
+                            int64_t F, int64_t N, int J, int K, double gamma, double alpha,
+                            double beta, uint64_t seed, double *W_samples, double *H_samples,
+                            int32_t *V_samples);
+
+/* ---- lower_bound_aspect with its eleven arguments (collapsed_gibbs_z_VB.cpp:339-369)
+ * for sizes where the E_Z cube (F x K x N, arma::cube layout) exists: the seven terms
+ * as the reference states them (:173-294).  terms7 = pW, pZ, pH, pV, qW, qZ, qH (may
+ * be NULL); *lb = pW + pZ + pH + pV - qW - qZ - qH.  qZ is NaN when E_Z holds an exact
+ * zero, as in the reference (:234).                                                 */
+int nbmf_lower_bound_aspect_full(nbmf_handle *h, const double *E_Z, const double *E_log_W,
+                                 const double *E_log_H, const double *E_log_1_H,
+                                 const double *gamma_vb, const double *alpha_vb,
+                                 const double *beta_vb, double alpha, double beta, double gamma,
+                                 const int32_t *V_colmajor, int64_t F, int64_t N, int K, double *lb,
+                                 double *terms7);
+
+/* ---- sample_gibbs_cpp (sample_gibbs.cpp:22-80) ---------------------------------
+ * one column's sweep over the one-hot matrix C (F x K int32, column-major) given W
+ * (paper orientation), h collapsed.  as_coded != 0: the reference as written -- its
+ * draw is never stored (:60-69), so the result is C / (number of kept states);
+ * as_coded == 0: the draw is stored (R sample_gibbs_Z, R/MCEM - sample_gibbs.R:1-37).
+ * C_mean F x K.                                                                     */
+int nbmf_sample_gibbs_cpp(nbmf_handle *h, const int32_t *v_n, const double *W, const int32_t *C,
+                          int64_t F, int K, double alpha, int iter, double burnin, uint64_t seed,
+                          int as_coded, double *C_mean);
+
+/* ---- collectives inside the library ("multi-GPU is internal to the
+ * handle") -------------------------------------------------------------------------
+ * One process per GPU: rank 0 fills id128 (128 bytes) with nbmf_comm_unique_id, ships it
+ * to the other ranks, every rank calls nbmf_comm_init_rank on its handle (created with
+ * nbmf_opts.n_global / n_offset describing its column block).  From then on the
+ * F x K Dirichlet-side statistic (int32 row counts for Gibbs) is summed over the ranks
+ * by the library itself (NCCL over NVLink), on a priority side stream beside the cols
+ * pass; the hook of nbmf_set_allreduce_hook is not consulted.                        */
+int nbmf_comm_unique_id(void *id128);
+int nbmf_comm_init_rank(nbmf_handle *h, const void *id128, int world, int rank);
+int nbmf_comm_destroy(nbmf_handle *h);
+int nbmf_comm_info(const nbmf_handle *h, int *rank, int *world);
+
+/* One process, several GPUs -- the reference's single R process
+ * (src/RcppExports.cpp:259-274): one handle, one NCCL rank and one host thread per
+ * device; the columns of V are cut into contiguous blocks (boundaries at multiples of
+ * 64; N >= 64 * n_devices).  opts->device is ignored, everything else applies to every
+ * handle.  The nbmf_group_* calls take and return WHOLE matrices.                    */
+typedef struct nbmf_group nbmf_group;
+int nbmf_group_create(nbmf_group **out, const nbmf_opts *opts, const int *devices, int n_devices);
+void nbmf_group_destroy(nbmf_group *g);
+int nbmf_group_size(const nbmf_group *g);
+nbmf_handle *nbmf_group_handle(nbmf_group *g, int rank);
+const char *nbmf_group_last_error(const nbmf_group *g);
+int nbmf_group_columns(const nbmf_group *g, int rank, int64_t *n_lo, int64_t *n_hi);
+int nbmf_group_set_data_i32(nbmf_group *g, const int32_t *V_colmajor, int64_t F, int64_t N);
+int nbmf_group_generate_synthetic(nbmf_group *g, int64_t F, int64_t N, int Ktrue, double a, double b,
+                                  uint64_t seed);
+int nbmf_group_init_from_labels(nbmf_group *g, const int32_t *Z_colmajor, int Kc);
+int nbmf_group_init_random_labels(nbmf_group *g, int Kc, uint64_t seed);
+int nbmf_group_vb_begin(nbmf_group *g, int K, double alpha, double beta, double gamma, int mean_params);
+int nbmf_group_vb_step(nbmf_group *g, int checklb);
+int nbmf_group_vb_end(nbmf_group *g, double *E_W, double *E_H, double *lowerbounds, int n_lb);
+int nbmf_group_synchronize(nbmf_group *g);
+/* VB_Aspect_Rcpp(V, Z, K, alpha, beta, gamma, iter, checklb) over all devices, one call */
+int nbmf_group_vb_aspect(nbmf_group *g, const int32_t *V_colmajor, const int32_t *Z_colmajor, int64_t F,
+                         int64_t N, int K, double alpha, double beta, double gamma, int iter,
+                         int checklb, double *E_W, double *E_H, double *lowerbounds);
+/* the same from host bit planes + host vbcounts (see nbmf_vb_aspect_bits) */
+int nbmf_group_vb_aspect_bits(nbmf_group *g, const uint32_t *vbits, int64_t F, int64_t N, int K,
+                              double alpha, double beta, double gamma, int iter, int checklb,
+                              const double *n_total, const double *f_ones, const double *f_zeros,
+                              double *E_W, double *E_H, double *lowerbounds);
+int nbmf_group_gibbs_dirber(nbmf_group *g, int K, double alpha, double beta, double gamma, int iter,
+                            double burnin, uint64_t seed, double *E_W, double *E_H);
 
 #ifdef __cplusplus
 }

@@ -13,13 +13,15 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(HERE, "libnbmf_cuda.so")
 
 NBMF_OK = 0
-PREC_AUTO, PREC_FP64, PREC_TENSOR, PREC_TENSOR_FAST = 0, 1, 2, 3
+PREC_AUTO, PREC_FP64, PREC_TENSOR, PREC_TENSOR_FAST, PREC_TENSOR_ACC, PREC_FP32 = 0, 1, 2, 3, 4, 5
+PATH_FP64, PATH_TENSOR, PATH_TENSOR_FAST, PATH_TENSOR_ACC, PATH_FP32 = 0, 1, 2, 3, 4
 DIRBER_EXACT_WAVEFRONT, DIRBER_CONTRACTION = 0, 1
 
 
 class NbmfOpts(C.Structure):
     _fields_ = [("device", C.c_int), ("precision", C.c_int), ("flush_interval", C.c_int),
-                ("pipe_block_cols", C.c_int), ("n_global", C.c_int64), ("n_offset", C.c_int64)]
+                ("pipe_block_cols", C.c_int), ("n_global", C.c_int64), ("n_offset", C.c_int64),
+                ("planned_iters", C.c_int), ("reserved", C.c_int)]
 
 
 class NbmfTiming(C.Structure):
@@ -77,6 +79,45 @@ SYMBOLS = {
     "nbmf_gibbs_sweep_given_W": (C.c_int, [_H, _ip, _dp, C.c_int64, C.c_int, C.c_double, C.c_int, C.c_double,
                                            C.c_uint64, _dp]),
     "nbmf_predictive_ll": (C.c_int, [_H, _dp, _dp, C.c_int, _ip, C.c_int64, C.c_int64, _dp, _lp]),
+    "nbmf_compute_expectation_W": (C.c_int, [_H, _ip, C.c_int64, C.c_int64, C.c_int, C.c_double, C.c_int, _dp]),
+    "nbmf_compute_expectation_H": (C.c_int, [_H, _ip, _ip, C.c_int64, C.c_int64, C.c_int, C.c_double, C.c_double, C.c_int, _dp]),
+    "nbmf_samples_VWH_DirBer": (C.c_int, [_H, _ip, _ip, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_double, C.c_double,
+                                          C.c_double, C.c_uint64, _dp, _dp, _ip]),
+    "nbmf_lower_bound_aspect_full": (C.c_int, [_H, _dp, _dp, _dp, _dp, _dp, _dp, _dp, C.c_double, C.c_double, C.c_double,
+                                               _ip, C.c_int64, C.c_int64, C.c_int, _dp, _dp]),
+    "nbmf_sample_gibbs_cpp": (C.c_int, [_H, _ip, _dp, _ip, C.c_int64, C.c_int, C.c_double, C.c_int, C.c_double, C.c_uint64,
+                                        C.c_int, _dp]),
+    "nbmf_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "nbmf_comm_init_rank": (C.c_int, [_H, C.c_void_p, C.c_int, C.c_int]),
+    "nbmf_comm_destroy": (C.c_int, [_H]),
+    "nbmf_comm_info": (C.c_int, [_H, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "nbmf_group_create": (C.c_int, [C.POINTER(_H), C.POINTER(NbmfOpts), C.POINTER(C.c_int), C.c_int]),
+    "nbmf_group_destroy": (None, [_H]),
+    "nbmf_group_size": (C.c_int, [_H]),
+    "nbmf_group_handle": (C.c_void_p, [_H, C.c_int]),
+    "nbmf_group_last_error": (C.c_char_p, [_H]),
+    "nbmf_group_columns": (C.c_int, [_H, C.c_int, _lp, _lp]),
+    "nbmf_group_set_data_i32": (C.c_int, [_H, _ip, C.c_int64, C.c_int64]),
+    "nbmf_group_generate_synthetic": (C.c_int, [_H, C.c_int64, C.c_int64, C.c_int, C.c_double, C.c_double, C.c_uint64]),
+    "nbmf_group_init_from_labels": (C.c_int, [_H, _ip, C.c_int]),
+    "nbmf_group_init_random_labels": (C.c_int, [_H, C.c_int, C.c_uint64]),
+    "nbmf_group_vb_begin": (C.c_int, [_H, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int]),
+    "nbmf_group_vb_step": (C.c_int, [_H, C.c_int]),
+    "nbmf_group_vb_end": (C.c_int, [_H, _dp, _dp, _dp, C.c_int]),
+    "nbmf_group_synchronize": (C.c_int, [_H]),
+    "nbmf_group_vb_aspect": (C.c_int, [_H, _ip, _ip, C.c_int64, C.c_int64, C.c_int, C.c_double, C.c_double, C.c_double,
+                                       C.c_int, C.c_int, _dp, _dp, _dp]),
+    "nbmf_group_vb_aspect_bits": (C.c_int, [_H, _up, C.c_int64, C.c_int64, C.c_int, C.c_double, C.c_double, C.c_double,
+                                            C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp]),
+    "nbmf_group_gibbs_dirber": (C.c_int, [_H, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_double,
+                                          C.c_uint64, _dp, _dp]),
+}
+
+# debug / measurement aids exported by the library but not part of include/nbmf_cuda.h
+DEBUG_SYMBOLS = {
+    "nbmf_debug_model_error": (C.c_double, [C.c_int, C.c_double, C.c_int]),
+    "nbmf_debug_rng_probe": (C.c_int, [_H, C.c_int, C.c_double, C.c_double, C.c_uint64, C.c_int64, _dp]),
+    "nbmf_debug_ffma_peak": (C.c_int, [_H, _dp]),
 }
 
 _lib = None
@@ -101,6 +142,10 @@ def load():
     lib = C.CDLL(SO_PATH)
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)  # AttributeError if the .so does not export it
+        fn.restype = res
+        fn.argtypes = args
+    for name, (res, args) in DEBUG_SYMBOLS.items():
+        fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
     _lib = lib

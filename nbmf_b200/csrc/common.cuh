@@ -45,22 +45,39 @@ struct nbmf_handle {
     int lbs_cap = 0;
     int32_t *Z = nullptr;                        // labels, column-major f + F*n (optional)
     void *stage = nullptr; size_t stage_bytes = 0;
+    void *io = nullptr; size_t io_bytes = 0;     // staging of host <-> device matrix transfers (layout change on the device)
+    cudaStream_t out_stream = nullptr;           // early download of E_W / E_H beside the last iteration
+    cudaEvent_t out_ev = nullptr;
+    double *early_EW = nullptr, *early_EH = nullptr;   // host destinations, armed for step `early_iter`
+    int early_iter = -1; bool early_done = false;
 
     // VB session (begin/step/end)
     bool vb_active = false;
     int vb_K = 0, vb_iter = 0, vb_mean_params = 0;
     double vb_alpha = 1, vb_beta = 1, vb_gamma = 1;
 
+    // contraction variant of the current session (nbmf_path), fixed by resolve_path()
+    int path_mode = 0;
+    int vb_horizon = 0;                          // VB updates planned from this start (AUTO precision)
+    int horizon_next = 0;                        // set by the single-call entry points for their nbmf_vb_begin
+
     // tensor path state (tensor_pass.cu)
     void *tp = nullptr;
 
     nbmf_allreduce_fn hook = nullptr; void *hook_ctx = nullptr;
+    // collectives owned by the library (nbmf_comm_init_rank / nbmf_group_create): an NCCL communicator
+    // over the ranks that share the columns of V; takes precedence over the hook
+    void *comm = nullptr;                        // ncclComm_t
+    int comm_rank = 0, comm_world = 1;
+    bool comm_owned = false;
+    void *hook_scratch = nullptr; size_t hook_scratch_bytes = 0;   // fp64 staging of non-fp64 exchanges through the hook
     nbmf_timing timing{};
     cudaEvent_t ev[8] = {};
     // exchange overlapped with the cols pass: side stream + begin / end events
     cudaStream_t xchg_stream = nullptr;
     cudaEvent_t xchg_ev[2] = {};
-    bool xchg_pending = false;
+    cudaEvent_t xchg_t[2] = {};                  // timing events around the collective on the side stream
+    bool xchg_pending = false, xchg_timed = false;
     // pipelined upload (nbmf_vb_aspect_bits): copy stream, one event per column block
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t pipe_ev[33] = {};

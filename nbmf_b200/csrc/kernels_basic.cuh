@@ -339,7 +339,6 @@ __global__ void finalize_stats_kernel(const double *__restrict__ U, const double
 //   row f (sb=1), W = A, bits packed along f; sel = mask & (v == b).
 // This is VB_Aspect_Rcpp's q(Z) loop (collapsed_gibbs_z_VB.cpp:447-465) with
 // the E_Z cube eliminated.
-// Thread layout: NKC = Kp/KC consecutive lanes share an owner lane and split k.
 // ---------------------------------------------------------------------------
 struct PassArgs {
     const double *U, *W;
@@ -350,10 +349,15 @@ struct PassArgs {
     double *sumlogD;
 };
 
-template <int KC>
-__global__ void __launch_bounds__(256) pass_fp64_kernel(PassArgs a)
+// SIMT form (FP64 or FP32 FMA pipe + warp shuffles): NKC = Kp/KC consecutive lanes share an owner
+// lane and split k, the dot product is finished with shfl.xor.  T = double: any Kp up to 512 (the
+// DMMA kernel of pass_mma64.cuh takes Kp <= 128); T = float: the small-K FFMA path of the north
+// star (NBMF_PREC_FP32) -- operands and accumulation in fp32, results handed back in fp64.
+template <typename T, int KC>
+__global__ void __launch_bounds__(256) pass_simt_kernel(PassArgs a)
 {
-    extern __shared__ double sm_w[]; // [TR*sb][Kp]
+    extern __shared__ unsigned char sm_w_raw[];
+    T *sm_w = reinterpret_cast<T *>(sm_w_raw); // [TR*sb][Kp]
     __shared__ double sh_red[32];
     const int Kp = a.Kp, NKC = Kp / KC, tid = threadIdx.x;
     const int kc = tid % NKC, ol = tid / NKC, OL = 256 / NKC;
@@ -361,11 +365,11 @@ __global__ void __launch_bounds__(256) pass_fp64_kernel(PassArgs a)
     const bool lane_ok = l < a.L;
     const int64_t orow = lane_ok ? l / a.ob : 0;
     const int bown = (int)(l % a.ob);
-    double u[KC], acc[KC];
+    T u[KC], acc[KC];
 #pragma unroll
     for (int i = 0; i < KC; i++) {
-        u[i] = lane_ok ? a.U[l * Kp + kc * KC + i] : 0.0;
-        acc[i] = 0.0;
+        u[i] = lane_ok ? (T)a.U[l * Kp + kc * KC + i] : (T)0;
+        acc[i] = (T)0;
     }
     double ell = 0.0;
     const int64_t s_begin = (int64_t)blockIdx.y * a.s_per_split;
@@ -376,7 +380,7 @@ __global__ void __launch_bounds__(256) pass_fp64_kernel(PassArgs a)
         __syncthreads();
         const double *src = a.W + r0 * sb * Kp;
         const int64_t valid = min((int64_t)tile_elems, (a.S - r0) * sb * Kp);
-        for (int i = tid; i < tile_elems; i += 256) sm_w[i] = (i < valid) ? src[i] : 0.0;
+        for (int i = tid; i < tile_elems; i += 256) sm_w[i] = (i < valid) ? (T)src[i] : (T)0;
         __syncthreads();
         uint32_t wv = 0, wm = 0;
         if (lane_ok) {
@@ -391,13 +395,13 @@ __global__ void __launch_bounds__(256) pass_fp64_kernel(PassArgs a)
             int c;
             if (sb == 2) c = 2 * j + v;
             else { c = j; act = act && (v == bown); }
-            const double *wrow = sm_w + c * Kp + kc * KC;
-            double d = 0.0;
+            const T *wrow = sm_w + c * Kp + kc * KC;
+            T d = (T)0;
 #pragma unroll
             for (int i = 0; i < KC; i++) d = fma(u[i], wrow[i], d);
             for (int o = NKC >> 1; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-            double R = act ? 1.0 / d : 0.0;
-            if (a.sumlogD != nullptr && act && kc == 0) ell += log(d);
+            const T R = act ? (T)1 / d : (T)0;
+            if (a.sumlogD != nullptr && act && kc == 0) ell += (double)log(d);
 #pragma unroll
             for (int i = 0; i < KC; i++) acc[i] = fma(R, wrow[i], acc[i]);
         }
@@ -405,10 +409,10 @@ __global__ void __launch_bounds__(256) pass_fp64_kernel(PassArgs a)
     if (lane_ok) {
         if (gridDim.y == 1) {
 #pragma unroll
-            for (int i = 0; i < KC; i++) a.G[l * Kp + kc * KC + i] = acc[i];
+            for (int i = 0; i < KC; i++) a.G[l * Kp + kc * KC + i] = (double)acc[i];
         } else {
 #pragma unroll
-            for (int i = 0; i < KC; i++) atomicAdd(&a.G[l * Kp + kc * KC + i], acc[i]);
+            for (int i = 0; i < KC; i++) atomicAdd(&a.G[l * Kp + kc * KC + i], (double)acc[i]);
         }
     }
     if (a.sumlogD != nullptr) {

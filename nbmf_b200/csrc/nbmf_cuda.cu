@@ -2,7 +2,10 @@
 // orchestration of the VB / CVB0 / Gibbs hot path.  No CPU fallback: every
 // compute entry point needs a CUDA device.
 #include "kernels_basic.cuh"
+#include "pass_mma64.cuh"
+#include "gibbs_fast.cuh"
 #include "tensor_pass.h"
+#include "host_common.h"
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -11,27 +14,6 @@
 #include <type_traits>
 #include <vector>
 
-#define CK(call) NBMF_CUDA_CHECK(h, call)
-#define LAUNCH_CHECK() CK(cudaGetLastError())
-
-static inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
-
-// device allocation that is released on every return path
-template <class T> struct DevBuf {
-    T *p = nullptr;
-    DevBuf() = default;
-    DevBuf(const DevBuf &) = delete;
-    DevBuf &operator=(const DevBuf &) = delete;
-    ~DevBuf() { if (p) cudaFree(p); }
-    cudaError_t alloc(size_t count) { return cudaMalloc((void **)&p, (count ? count : 1) * sizeof(T)); }
-    operator T *() const { return p; }
-};
-
-static int fail(nbmf_handle *h, int code, const char *msg)
-{
-    if (h) h->err = msg;
-    return code;
-}
 
 // ---------------------------------------------------------------------------
 // lifecycle
@@ -102,11 +84,17 @@ extern "C" void nbmf_destroy(nbmf_handle *h)
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     free_data(h); free_model(h);
-    cudaFree(h->scal); cudaFree(h->lbs); cudaFree(h->stage);
+    cudaFree(h->scal); cudaFree(h->lbs); cudaFree(h->stage); cudaFree(h->io);
+    if (h->out_stream) { cudaStreamDestroy(h->out_stream); cudaEventDestroy(h->out_ev); }
     for (int i = 0; i < 8; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     for (int i = 0; i < 33; i++) if (h->pipe_ev[i]) cudaEventDestroy(h->pipe_ev[i]);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
-    if (h->xchg_stream) { cudaStreamDestroy(h->xchg_stream); cudaEventDestroy(h->xchg_ev[0]); cudaEventDestroy(h->xchg_ev[1]); }
+    if (h->xchg_stream) {
+        cudaStreamDestroy(h->xchg_stream); cudaEventDestroy(h->xchg_ev[0]); cudaEventDestroy(h->xchg_ev[1]);
+        cudaEventDestroy(h->xchg_t[0]); cudaEventDestroy(h->xchg_t[1]);
+    }
+    nbmf_comm_release(h);
+    cudaFree(h->hook_scratch);
     cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -124,6 +112,7 @@ extern "C" int nbmf_set_allreduce_hook(nbmf_handle *h, nbmf_allreduce_fn fn, voi
 {
     if (!h) return NBMF_ERR_ARG;
     h->hook = fn; h->hook_ctx = ctx;
+    tp_invalidate_data(h);   // the exact row counts of the tensor path were summed with the previous set of ranks
     return NBMF_OK;
 }
 extern "C" int nbmf_get_timing(const nbmf_handle *h, nbmf_timing *out)
@@ -155,33 +144,37 @@ static int ensure_stage(nbmf_handle *h, size_t bytes)
 
 static int exchange(nbmf_handle *h, double *buf, size_t count)
 {
-    if (!h->hook) return NBMF_OK;
-    int rc = h->hook(h->hook_ctx, (void *)buf, count, (void *)h->stream);
-    if (rc != 0) return fail(h, NBMF_ERR_STATE, "allreduce hook failed");
-    return NBMF_OK;
+    if (!nbmf_sharded(h)) return NBMF_OK;
+    return nbmf_sum_ranks(h, buf, count, 0, h->stream);
 }
 
 // The same exchange started on a side stream behind the current point of the main stream, so
 // that whatever the main stream launches next overlaps it; exchange_end makes the main stream
 // wait for the result.  The side stream has the highest priority: the collective's few CTAs are
 // placed before the persistent contraction kernel that follows, whose work queue absorbs the
-// SMs that come late.
+// SMs that come late.  The collective itself is bracketed by events on the side stream
+// (timing.exchange_ms is its device time, not the time the main stream spent waiting).
 static int exchange_begin(nbmf_handle *h, double *buf, size_t count)
 {
-    if (!h->hook) return NBMF_OK;
+    if (!nbmf_sharded(h)) return NBMF_OK;
     if (!h->xchg_stream) {
         int lo = 0, hi = 0;
         CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         CK(cudaStreamCreateWithPriority(&h->xchg_stream, cudaStreamNonBlocking, hi));
         CK(cudaEventCreateWithFlags(&h->xchg_ev[0], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&h->xchg_ev[1], cudaEventDisableTiming));
+        CK(cudaEventCreate(&h->xchg_t[0]));
+        CK(cudaEventCreate(&h->xchg_t[1]));
     }
     CK(cudaEventRecord(h->xchg_ev[0], h->stream));
     CK(cudaStreamWaitEvent(h->xchg_stream, h->xchg_ev[0], 0));
-    int rc = h->hook(h->hook_ctx, buf, count, (void *)h->xchg_stream);
-    if (rc != 0) return fail(h, NBMF_ERR_CUDA, "all-reduce hook failed");
+    CK(cudaEventRecord(h->xchg_t[0], h->xchg_stream));
+    int rc = nbmf_sum_ranks(h, buf, count, 0, h->xchg_stream);
+    if (rc) return rc;
+    CK(cudaEventRecord(h->xchg_t[1], h->xchg_stream));
     CK(cudaEventRecord(h->xchg_ev[1], h->xchg_stream));
     h->xchg_pending = true;
+    h->xchg_timed = true;
     // The collective's kernel and the cols pass become runnable at the same moment; if the
     // persistent cols kernel is placed first it holds every SM and the collective runs after it
     // instead of beside it.  20 us on the main stream decide that race (NBMF_XCHG_PAUSE_US).
@@ -282,7 +275,10 @@ extern "C" int nbmf_set_data_i32(nbmf_handle *h, const int32_t *V, int64_t F, in
     unsigned long long res[2];
     CK(cudaMemcpyAsync(res, cnt, 16, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    if (res[1]) return fail(h, NBMF_ERR_ARG, "V contains values other than 0, 1 and NA");
+    if (res[1]) {   // part of the planes has been overwritten: leave the handle without data rather than with a mixture
+        free_data(h);
+        return fail(h, NBMF_ERR_ARG, "V contains values other than 0, 1 and NA");
+    }
     h->nobs = (int64_t)res[0];
     h->has_na = (h->nobs != F * N);
     rc = build_row_planes(h);
@@ -374,8 +370,7 @@ extern "C" int nbmf_generate_synthetic(nbmf_handle *h, int64_t F, int64_t N, int
 // ---------------------------------------------------------------------------
 static void choose_kchunks(int K, int *KC, int *NKC)
 {
-    if (K <= 4) { *KC = 4; *NKC = 1; }
-    else if (K <= 8) { *KC = 8; *NKC = 1; }
+    if (K <= 8) { *KC = 8; *NKC = 1; }   // Kp >= 8: one k tile of the DMMA kernel
     else {
         *KC = 16;
         int n = 1;
@@ -474,27 +469,55 @@ extern "C" int nbmf_init_random_labels(nbmf_handle *h, int Kc, uint64_t seed)
     return NBMF_OK;
 }
 
-static int upload_rows(nbmf_handle *h, const double *src, int64_t rows, int K, double *dst, int mul,
-                       int add)
+static int ensure_io(nbmf_handle *h, size_t bytes)
 {
-    int rc = ensure_stage(h, (size_t)rows * K * 8);
-    if (rc) return rc;
-    CK(cudaMemcpyAsync(h->stage, src, (size_t)rows * K * 8, cudaMemcpyHostToDevice, h->stream));
-    colmajor_to_rows_kernel<<<nblk(rows * K, 256), 256, 0, h->stream>>>((const double *)h->stage, rows,
-                                                                        K, dst, h->Kp, mul, add);
+    if (h->io_bytes >= bytes) return NBMF_OK;
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->out_stream) CK(cudaStreamSynchronize(h->out_stream));
+    cudaFree(h->io); h->io = nullptr; h->io_bytes = 0;
+    if (cudaMalloc(&h->io, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(h, NBMF_ERR_OOM, "device staging buffer allocation failed");
+    }
+    h->io_bytes = bytes;
+    return NBMF_OK;
+}
+
+// host column-major [ld x K] (rows `rows` of it) -> device row-major [rows][Kp], asynchronously on `st`,
+// through the staging area at byte offset `off` of h->io (the caller sized it with ensure_io)
+static int upload_rows_async(nbmf_handle *h, const double *src, int64_t ld, int64_t rows, int K, double *dst,
+                             int mul, int add, size_t off, cudaStream_t st)
+{
+    double *stg = (double *)((char *)h->io + off);
+    if (ld == rows) CK(cudaMemcpyAsync(stg, src, (size_t)rows * K * 8, cudaMemcpyHostToDevice, st));
+    else CK(cudaMemcpy2DAsync(stg, (size_t)rows * 8, src, (size_t)ld * 8, (size_t)rows * 8, (size_t)K, cudaMemcpyHostToDevice, st));
+    colmajor_to_rows_kernel<<<nblk(rows * K, 256), 256, 0, st>>>(stg, rows, K, dst, h->Kp, mul, add);
     LAUNCH_CHECK();
+    return NBMF_OK;
+}
+static int download_rows_async(nbmf_handle *h, const double *src, int64_t rows, int K, double *dst, int64_t ld,
+                               int mul, int add, size_t off, cudaStream_t st)
+{
+    double *stg = (double *)((char *)h->io + off);
+    rows_to_colmajor_kernel<<<nblk(rows * K, 256), 256, 0, st>>>(src, rows, K, stg, h->Kp, mul, add);
+    LAUNCH_CHECK();
+    if (ld == rows) CK(cudaMemcpyAsync(dst, stg, (size_t)rows * K * 8, cudaMemcpyDeviceToHost, st));
+    else CK(cudaMemcpy2DAsync(dst, (size_t)ld * 8, stg, (size_t)rows * 8, (size_t)rows * 8, (size_t)K, cudaMemcpyDeviceToHost, st));
+    return NBMF_OK;
+}
+static int upload_rows(nbmf_handle *h, const double *src, int64_t rows, int K, double *dst, int mul, int add)
+{
+    int rc = ensure_io(h, (size_t)rows * K * 8);
+    if (rc) return rc;
+    if ((rc = upload_rows_async(h, src, rows, rows, K, dst, mul, add, 0, h->stream))) return rc;
     CK(cudaStreamSynchronize(h->stream));
     return NBMF_OK;
 }
-static int download_rows(nbmf_handle *h, const double *src, int64_t rows, int K, double *dst, int mul,
-                         int add)
+static int download_rows(nbmf_handle *h, const double *src, int64_t rows, int K, double *dst, int mul, int add)
 {
-    int rc = ensure_stage(h, (size_t)rows * K * 8);
+    int rc = ensure_io(h, (size_t)rows * K * 8);
     if (rc) return rc;
-    rows_to_colmajor_kernel<<<nblk(rows * K, 256), 256, 0, h->stream>>>(src, rows, K, (double *)h->stage,
-                                                                        h->Kp, mul, add);
-    LAUNCH_CHECK();
-    CK(cudaMemcpyAsync(dst, h->stage, (size_t)rows * K * 8, cudaMemcpyDeviceToHost, h->stream));
+    if ((rc = download_rows_async(h, src, rows, K, dst, rows, mul, add, 0, h->stream))) return rc;
     CK(cudaStreamSynchronize(h->stream));
     return NBMF_OK;
 }
@@ -519,6 +542,8 @@ extern "C" int nbmf_get_stats(nbmf_handle *h, int Kc, double *n_total, double *f
     if (!h->statF || Kc != h->Kc) return fail(h, NBMF_ERR_STATE, "no statistics with this Kc");
     CK(cudaSetDevice(h->device));
     int rc;
+    CK(cudaStreamSynchronize(h->stream));
+    if ((rc = tp_check_error(h))) return rc;   // an aborted tensor pass leaves garbage behind
     if (n_total && (rc = download_rows(h, h->statF, h->F, Kc, n_total, 1, 0))) return rc;
     if (f_ones && (rc = download_rows(h, h->statN, h->N, Kc, f_ones, 2, 1))) return rc;
     if (f_zeros && (rc = download_rows(h, h->statN, h->N, Kc, f_zeros, 2, 0))) return rc;
@@ -530,23 +555,93 @@ extern "C" int nbmf_get_stats(nbmf_handle *h, int Kc, double *n_total, double *f
 // ---------------------------------------------------------------------------
 static bool use_tensor_path(const nbmf_handle *h)
 {
-    int p = h->opts.precision;
-    if (p == NBMF_PREC_FP64) return false;
-    if (p == NBMF_PREC_TENSOR || p == NBMF_PREC_TENSOR_FAST) return true;
-    return tp_supported(h); // AUTO
+    return h->path_mode == NBMF_PATH_TENSOR || h->path_mode == NBMF_PATH_TENSOR_FAST || h->path_mode == NBMF_PATH_TENSOR_ACC;
 }
 
-template <int KC>
-static cudaError_t launch_pass(const PassArgs &a, dim3 grid, size_t smem, cudaStream_t s)
+// Fixes the contraction variant of a session from the precision option, K, the sizes and -- under
+// AUTO -- the number of updates the caller plans (the f16 variants' error grows with the iteration
+// count): must run before anything asks use_tensor_path().
+static void resolve_path(nbmf_handle *h, int K, int horizon)
 {
-    cudaError_t e = cudaFuncSetAttribute(pass_fp64_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int p = h->opts.precision;
+    if (horizon <= 0) horizon = h->opts.planned_iters > 0 ? h->opts.planned_iters : 100;   // VB_Aspect_Rcpp's default iter
+    h->vb_horizon = horizon;
+    if (p == NBMF_PREC_FP64) h->path_mode = NBMF_PATH_FP64;
+    else if (p == NBMF_PREC_FP32) h->path_mode = NBMF_PATH_FP32;
+    else if (p == NBMF_PREC_TENSOR) h->path_mode = NBMF_PATH_TENSOR;
+    else if (p == NBMF_PREC_TENSOR_FAST) h->path_mode = NBMF_PATH_TENSOR_FAST;
+    else if (p == NBMF_PREC_TENSOR_ACC) h->path_mode = NBMF_PATH_TENSOR_ACC;
+    else h->path_mode = tp_auto_mode(h, K, horizon);
+}
+
+template <typename T, int KC>
+static cudaError_t launch_simt(const PassArgs &a, dim3 grid, size_t smem, cudaStream_t s)
+{
+    cudaError_t e = cudaFuncSetAttribute(pass_simt_kernel<T, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    pass_fp64_kernel<KC><<<grid, 256, smem, s>>>(a);
+    pass_simt_kernel<T, KC><<<grid, 256, smem, s>>>(a);
     return cudaGetLastError();
 }
 
-// owner_rows != 0: owner = rows f, output GF; else owner = (n,b) lanes, output GN
-static int run_pass_fp64(nbmf_handle *h, int owner_rows, double *sumlogD)
+template <int KP>
+static cudaError_t launch_mma64(const Mma64Args &a, dim3 grid, bool rows, bool want_log, cudaStream_t s)
+{
+    const size_t smem = Mma64Cfg<KP>::SMEM;
+    cudaError_t e;
+    if (rows && want_log) {
+        e = cudaFuncSetAttribute(pass_mma64_kernel<KP, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) pass_mma64_kernel<KP, true, true><<<grid, 256, smem, s>>>(a);
+    } else if (rows) {
+        e = cudaFuncSetAttribute(pass_mma64_kernel<KP, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) pass_mma64_kernel<KP, true, false><<<grid, 256, smem, s>>>(a);
+    } else {
+        e = cudaFuncSetAttribute(pass_mma64_kernel<KP, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) pass_mma64_kernel<KP, false, false><<<grid, 256, smem, s>>>(a);
+    }
+    return e != cudaSuccess ? e : cudaGetLastError();
+}
+
+// FP64 pass on the DMMA pipe (pass_mma64.cuh), Kp in {8, 16, 32, 64, 128}
+static int run_pass_mma64(nbmf_handle *h, int owner_rows, double *sumlogD)
+{
+    Mma64Args a{};
+    a.sumlogD = sumlogD;
+    if (owner_rows) {
+        a.U = h->A; a.W = h->BB; a.G = h->GF;
+        a.vbits = h->vr; a.mbits = h->has_na ? h->mr : nullptr;
+        a.words = h->Nw; a.L = h->F; a.S_rows = 2 * h->N; a.ob = 1; a.sb = 2;
+    } else {
+        a.U = h->BB; a.W = h->A; a.G = h->GN;
+        a.vbits = h->vc; a.mbits = h->has_na ? h->mc : nullptr;
+        a.words = h->Fw; a.L = 2 * h->N; a.S_rows = h->F; a.ob = 2; a.sb = 1;
+    }
+    const int64_t bx = (a.L + 63) / 64;
+    const int64_t steps = (a.S_rows + 63) / 64;
+    // enough blocks for a few waves; a split streams at least 8 steps so that the owner tile load amortises
+    const int64_t want = 4ll * h->sm_count;
+    int64_t splits = std::max<int64_t>(1, std::min<int64_t>((want + bx - 1) / bx, (steps + 7) / 8));
+    a.rows_per_split = ((steps + splits - 1) / splits) * 64;
+    splits = (a.S_rows + a.rows_per_split - 1) / a.rows_per_split;
+    if (splits > 1) CK(cudaMemsetAsync(a.G, 0, (size_t)a.L * h->Kp * 8, h->stream));
+    dim3 grid((unsigned)bx, (unsigned)splits);
+    cudaError_t e;
+    const bool wl = sumlogD != nullptr;
+    switch (h->Kp) {
+    case 8: e = launch_mma64<8>(a, grid, owner_rows, wl, h->stream); break;
+    case 16: e = launch_mma64<16>(a, grid, owner_rows, wl, h->stream); break;
+    case 32: e = launch_mma64<32>(a, grid, owner_rows, wl, h->stream); break;
+    case 64: e = launch_mma64<64>(a, grid, owner_rows, wl, h->stream); break;
+    case 128: e = launch_mma64<128>(a, grid, owner_rows, wl, h->stream); break;
+    default: return fail(h, NBMF_ERR_STATE, "internal: DMMA pass with Kp > 128");
+    }
+    CK(e);
+    h->timing.launches += 1 + (splits > 1);
+    return NBMF_OK;
+}
+
+// owner_rows != 0: owner = rows f, output GF; else owner = (n,b) lanes, output GN.
+// fp32 = the FFMA variant (NBMF_PREC_FP32); fp64 SIMT serves Kp > 128 (and NBMF_FP64_KERNEL=simt).
+static int run_pass_simt(nbmf_handle *h, int owner_rows, double *sumlogD, bool fp32)
 {
     PassArgs a{};
     a.Kp = h->Kp;
@@ -560,10 +655,11 @@ static int run_pass_fp64(nbmf_handle *h, int owner_rows, double *sumlogD)
         a.vbits = h->vc; a.mbits = h->has_na ? h->mc : nullptr;
         a.words = h->Fw; a.L = 2 * h->N; a.S = h->F; a.ob = 2; a.sb = 1;
     }
+    const size_t esz = fp32 ? 4 : 8;
     int TR = 32;
-    while ((size_t)TR * a.sb * a.Kp * 8 > 65536 && TR > 1) TR >>= 1;
+    while ((size_t)TR * a.sb * a.Kp * esz > 65536 && TR > 1) TR >>= 1;
     a.TR = TR;
-    size_t smem = (size_t)TR * a.sb * a.Kp * 8;
+    size_t smem = (size_t)TR * a.sb * a.Kp * esz;
     const int OL = 256 / h->NKC;
     int64_t bx = (a.L + OL - 1) / OL;
     int64_t want = 4ll * h->sm_count;
@@ -573,9 +669,13 @@ static int run_pass_fp64(nbmf_handle *h, int owner_rows, double *sumlogD)
     if (splits > 1) CK(cudaMemsetAsync(a.G, 0, (size_t)a.L * a.Kp * 8, h->stream));
     dim3 grid((unsigned)bx, (unsigned)splits);
     cudaError_t e;
-    if (h->KC == 4) e = launch_pass<4>(a, grid, smem, h->stream);
-    else if (h->KC == 8) e = launch_pass<8>(a, grid, smem, h->stream);
-    else e = launch_pass<16>(a, grid, smem, h->stream);
+    if (fp32) {
+        if (h->KC == 8) e = launch_simt<float, 8>(a, grid, smem, h->stream);
+        else e = launch_simt<float, 16>(a, grid, smem, h->stream);
+    } else {
+        if (h->KC == 8) e = launch_simt<double, 8>(a, grid, smem, h->stream);
+        else e = launch_simt<double, 16>(a, grid, smem, h->stream);
+    }
     CK(e);
     h->timing.launches += 1 + (splits > 1);
     return NBMF_OK;
@@ -584,7 +684,10 @@ static int run_pass_fp64(nbmf_handle *h, int owner_rows, double *sumlogD)
 static int run_pass(nbmf_handle *h, int owner_rows, double *sumlogD)
 {
     if (use_tensor_path(h)) return tp_pass(h, owner_rows, sumlogD);
-    return run_pass_fp64(h, owner_rows, sumlogD);
+    if (h->path_mode == NBMF_PATH_FP32) return run_pass_simt(h, owner_rows, sumlogD, true);
+    static const bool force_simt = [] { const char *v = getenv("NBMF_FP64_KERNEL"); return v && strcmp(v, "simt") == 0; }();
+    if (h->Kp <= 128 && !force_simt) return run_pass_mma64(h, owner_rows, sumlogD);
+    return run_pass_simt(h, owner_rows, sumlogD, false);
 }
 
 static int run_params(nbmf_handle *h, int K, double alpha, double beta, double gamma, int mean_mode,
@@ -613,13 +716,17 @@ extern "C" int nbmf_vb_begin(nbmf_handle *h, int K, double alpha, double beta, d
         return fail(h, NBMF_ERR_STATE, "statistics missing or initialised with a different K");
     if (!(alpha > 0) || !(beta > 0) || !(gamma > 0)) return fail(h, NBMF_ERR_ARG, "priors must be > 0");
     CK(cudaSetDevice(h->device));
+    resolve_path(h, K, h->horizon_next);
+    h->horizon_next = 0;
     if (use_tensor_path(h)) {
         int rc = tp_prepare(h);
         if (rc) return rc;
     }
+    h->xchg_timed = false;
     h->vb_active = true; h->vb_K = K; h->vb_iter = 0; h->vb_mean_params = mean_params;
     h->vb_alpha = alpha; h->vb_beta = beta; h->vb_gamma = gamma;
     h->timing = nbmf_timing{};
+    h->timing.path = h->path_mode;
     CK(cudaMemsetAsync(h->scal, 0, SC_COUNT * sizeof(double), h->stream));
     CK(cudaEventRecord(h->ev[0], h->stream));
     return NBMF_OK;
@@ -646,6 +753,19 @@ extern "C" int nbmf_vb_step(nbmf_handle *h, int checklb)
     CK(cudaEventRecord(h->ev[1], h->stream));
     if ((rc = run_params(h, h->vb_K, h->vb_alpha, h->vb_beta, h->vb_gamma, h->vb_mean_params, checklb))) return rc;
     CK(cudaEventRecord(h->ev[2], h->stream));
+    if (h->early_iter == i && (h->early_EW || h->early_EH)) {
+        // E_W / E_H of the call are the parameters at the top of its LAST iteration
+        // (collapsed_gibbs_z_VB.cpp:507-514): final as soon as that iteration's parameter kernels
+        // have run, so their download overlaps the contraction (and, full duplex, the upload of V)
+        const size_t off = (size_t)(h->F + 2 * h->N) * h->vb_K * 8;   // behind the statistics' staging area
+        CK(cudaEventRecord(h->out_ev, h->stream));
+        CK(cudaStreamWaitEvent(h->out_stream, h->out_ev, 0));
+        if (h->early_EW && (rc = download_rows_async(h, h->EW, h->F, h->vb_K, h->early_EW, h->F, 1, 0, off, h->out_stream))) return rc;
+        if (h->early_EH && (rc = download_rows_async(h, h->EH, h->N, h->vb_K, h->early_EH, h->N, 1, 0,
+                                                     off + (size_t)h->F * h->vb_K * 8, h->out_stream))) return rc;
+        h->early_done = true;
+    }
+    if (h->pipe_blocks > 0 && !use_tensor_path(h)) { h->pipe_blocks = 0; return fail(h, NBMF_ERR_STATE, "internal: pipelined upload without the tensor path"); }
     if (h->pipe_blocks > 0) {
         // first step of nbmf_vb_aspect_bits: both passes, column block by column block, as the
         // upload of V arrives; reductions, exchange and corrections follow once
@@ -708,6 +828,8 @@ extern "C" int nbmf_vb_end(nbmf_handle *h, double *E_W, double *E_H, double *low
         cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]); h->timing.params_ms = ms;
         cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]); h->timing.pass_rows_ms = ms;
         cudaEventElapsedTime(&ms, h->ev[3], h->ev[4]); h->timing.exchange_ms = ms;
+        if (h->xchg_timed && cudaEventElapsedTime(&ms, h->xchg_t[0], h->xchg_t[1]) == cudaSuccess)
+            h->timing.exchange_ms = ms;   // overlapped exchange: the collective's own device time on the side stream
         cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]); h->timing.pass_cols_ms = ms;
     }
     int rc;
@@ -719,8 +841,14 @@ extern "C" int nbmf_vb_end(nbmf_handle *h, double *E_W, double *E_H, double *low
     if (h->vb_iter == 0) { // E_W / E_H of the current statistics
         if ((rc = run_params(h, K, h->vb_alpha, h->vb_beta, h->vb_gamma, h->vb_mean_params, 0))) return rc;
     }
-    if (E_W && (rc = download_rows(h, h->EW, h->F, K, E_W, 1, 0))) return rc;
-    if (E_H && (rc = download_rows(h, h->EH, h->N, K, E_H, 1, 0))) return rc;
+    if (h->early_done && h->early_EW == E_W && h->early_EH == E_H) {
+        CK(cudaStreamSynchronize(h->out_stream));   // already on their way since the last iteration's parameter kernels
+    } else {
+        if (h->early_done) CK(cudaStreamSynchronize(h->out_stream));
+        if (E_W && (rc = download_rows(h, h->EW, h->F, K, E_W, 1, 0))) return rc;
+        if (E_H && (rc = download_rows(h, h->EH, h->N, K, E_H, 1, 0))) return rc;
+    }
+    h->early_done = false; h->early_iter = -1; h->early_EW = h->early_EH = nullptr;
     if (lowerbounds && n_lb > 0) {
         int n = std::min(n_lb, h->vb_iter);
         std::vector<double> a((size_t)std::max(1, n) * 3, 0.0);
@@ -748,6 +876,7 @@ extern "C" int nbmf_vb_get_lb_terms(nbmf_handle *h, double *terms3, int n_iter)
     if (!h || !terms3) return NBMF_ERR_ARG;
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->stream));
+    { int rc0 = tp_check_error(h); if (rc0) return rc0; }
     int n = std::min(n_iter, std::min(h->vb_iter, h->lbs_cap));
     for (int i = 0; i < 3 * n_iter; i++) terms3[i] = 0.0;
     if (n > 0) CK(cudaMemcpy(terms3, h->lbs, (size_t)n * 24, cudaMemcpyDeviceToHost));
@@ -759,6 +888,7 @@ extern "C" int nbmf_vb_aspect(nbmf_handle *h, int K, double alpha, double beta, 
 {
     if (!h) return NBMF_ERR_ARG;
     if (iter < 0) return fail(h, NBMF_ERR_ARG, "iter < 0");
+    h->horizon_next = std::max(1, iter);   // AUTO precision: this call's own iteration count
     int rc = nbmf_vb_begin(h, K, alpha, beta, gamma, 0);
     if (rc) return rc;
     for (int i = 0; i < iter; i++)
@@ -769,36 +899,77 @@ extern "C" int nbmf_vb_aspect(nbmf_handle *h, int K, double alpha, double beta, 
 // VB_Aspect_Rcpp with V given as host bit planes and the initial statistics as host arrays: one
 // call = upload + iter iterations + results.  The upload is cut into column blocks on a copy
 // stream and the first iteration consumes the blocks as they land (both passes of a block need
-// nothing but that block's columns), so the PCIe transfer overlaps the contraction.
+// nothing but that block's columns), so the PCIe transfer overlaps the contraction; the blocks
+// shrink towards the end so that little compute is left when the last one has landed.  E_W / E_H
+// leave beside the last iteration (see nbmf_vb_step).  With a communicator the row-side arrays are
+// the root's: n_total is read on rank 0 and broadcast over NVLink, E_W may be NULL elsewhere.
 extern "C" int nbmf_vb_aspect_bits(nbmf_handle *h, const uint32_t *vbits, int64_t F, int64_t N, int K,
                                    double alpha, double beta, double gamma, int iter, int checklb,
                                    const double *n_total, const double *f_ones, const double *f_zeros,
                                    double *E_W, double *E_H, double *lowerbounds)
 {
     if (!h) return NBMF_ERR_ARG;
-    if (!vbits || F <= 0 || N <= 0 || iter < 0) return fail(h, NBMF_ERR_ARG, "nbmf_vb_aspect_bits: bad arguments");
+    if (!vbits || F <= 0 || N <= 0 || iter < 0 || K <= 0) return fail(h, NBMF_ERR_ARG, "nbmf_vb_aspect_bits: bad arguments");
+    const bool root = h->comm == nullptr || h->comm_rank == 0;
+    if (!f_ones || !f_zeros || (root && !n_total)) return fail(h, NBMF_ERR_ARG, "nbmf_vb_aspect_bits: NULL statistics");
     CK(cudaSetDevice(h->device));
-    // block size: about N/8 columns (a multiple of 64 = one owner tile of the cols pass = two
-    // steps of the rows pass); at most 32 blocks
-    int64_t blk = h->opts.pipe_block_cols > 0 ? (int64_t)h->opts.pipe_block_cols
-                                              : std::max<int64_t>(2048, ((N + 7) / 8 + 2047) / 2048 * 2048);
-    blk = std::max<int64_t>(64, (blk + 63) / 64 * 64);
-    while ((N + blk - 1) / blk > 32) blk *= 2;
-    const int nb = (int)((N + blk - 1) / blk);
     int rc = alloc_planes(h, F, N);
     if (rc) return rc;
     h->has_na = false; h->nobs = F * N;
+    // the contraction variant follows from THIS call's K and iteration count (not from whatever
+    // model the handle held before)
+    resolve_path(h, K, std::max(1, iter));
+    // column blocks: multiples of 64 columns (one owner tile of the cols pass = two steps of the rows
+    // pass); seven of about N/8, then a tail of N/16, N/32, N/32
+    int64_t unit = h->opts.pipe_block_cols > 0 ? (int64_t)h->opts.pipe_block_cols
+                                               : std::max<int64_t>(2048, ((N + 7) / 8 + 2047) / 2048 * 2048);
+    unit = std::max<int64_t>(64, (unit + 63) / 64 * 64);
+    while ((N + unit - 1) / unit > 24) unit *= 2;
+    int nb = 0;
+    h->pipe_n0[0] = 0;
+    for (int64_t c = 0; c < N && nb < 32;) {
+        int64_t len = unit;
+        const int64_t left = N - c;
+        if (h->opts.pipe_block_cols <= 0 && left <= unit && unit >= 4 * 2048) {   // the tail: halves, quarters
+            len = left > unit / 2 ? unit / 2 : (left > unit / 4 ? unit / 4 : left);
+            len = std::max<int64_t>(64, (len + 63) / 64 * 64);
+        }
+        c = std::min(N, c + len);
+        h->pipe_n0[++nb] = c;
+    }
+    if (h->pipe_n0[nb] < N) h->pipe_n0[nb] = N;
     const bool pipelined = iter >= 1 && nb >= 2 && use_tensor_path(h);
     if (!pipelined) {
         if ((rc = nbmf_set_data_bits(h, vbits, nullptr, F, N))) return rc;
-        if ((rc = nbmf_set_stats(h, K, n_total, f_ones, f_zeros))) return rc;
+        if (h->comm && h->comm_world > 1) {
+            // install the local statistics, then the root's row-side statistic over NVLink
+            std::vector<double> zero;
+            const double *nt = n_total;
+            if (!nt) { zero.assign((size_t)F * K, 0.0); nt = zero.data(); }
+            if ((rc = nbmf_set_stats(h, K, nt, f_ones, f_zeros))) return rc;
+            if ((rc = nbmf_bcast_root(h, h->statF, (size_t)F * h->Kp * 8, h->stream))) return rc;
+        } else if ((rc = nbmf_set_stats(h, K, n_total, f_ones, f_zeros))) return rc;
         return nbmf_vb_aspect(h, K, alpha, beta, gamma, iter, checklb, E_W, E_H, lowerbounds, nullptr);
     }
     tp_invalidate_data(h);
     if (!h->copy_stream) CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-    for (int b = 0; b <= nb; b++) h->pipe_n0[b] = std::min<int64_t>(N, (int64_t)b * blk);
-    // the statistics first (the parameters of the first iteration need all of them), then V
-    if ((rc = nbmf_set_stats(h, K, n_total, f_ones, f_zeros))) return rc;   // synchronises h->stream
+    if (!h->out_stream) {
+        CK(cudaStreamCreateWithFlags(&h->out_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&h->out_ev, cudaEventDisableTiming));
+    }
+    // the statistics first (the parameters of the first iteration need all of them), asynchronously,
+    // each array through its own part of the staging area; then V, block by block, on the copy stream
+    h->Kc = 0;
+    if ((rc = ensure_model(h, K))) return rc;
+    const size_t fk = (size_t)F * K * 8, nk = (size_t)N * K * 8;
+    if ((rc = ensure_io(h, 2 * (fk + 2 * nk)))) return rc;   // uploads in [0, fk + 2 nk), early outputs behind them
+    if (root && (rc = upload_rows_async(h, n_total, F, F, K, h->statF, 1, 0, 0, h->stream))) return rc;
+    if ((rc = upload_rows_async(h, f_ones, N, N, K, h->statN, 2, 1, fk, h->stream))) return rc;
+    if ((rc = upload_rows_async(h, f_zeros, N, N, K, h->statN, 2, 0, fk + nk, h->stream))) return rc;
+    if (h->comm && h->comm_world > 1 && (rc = nbmf_bcast_root(h, h->statF, (size_t)F * h->Kp * 8, h->stream))) return rc;
+    // the first block's copy is queued behind the statistics (one PCIe direction serves both)
+    CK(cudaEventRecord(h->out_ev, h->stream));
+    CK(cudaStreamWaitEvent(h->copy_stream, h->out_ev, 0));
     const int64_t fw_in = (F + 31) / 32;
     for (int b = 0; b < nb; b++) {
         const int64_t c0 = h->pipe_n0[b], c1 = h->pipe_n0[b + 1];
@@ -807,19 +978,30 @@ extern "C" int nbmf_vb_aspect_bits(nbmf_handle *h, const uint32_t *vbits, int64_
                              (size_t)fw_in * 4, (size_t)(c1 - c0), cudaMemcpyHostToDevice, h->copy_stream));
         CK(cudaEventRecord(h->pipe_ev[b], h->copy_stream));
     }
+    // from here on the host buffer is in use by the copy stream: every exit synchronises it, and a
+    // failure leaves the handle without data rather than with half-built planes
+    auto bail = [&](int code) {
+        cudaStreamSynchronize(h->copy_stream);
+        cudaStreamSynchronize(h->stream);
+        if (h->out_stream) cudaStreamSynchronize(h->out_stream);
+        h->vb_active = false; h->pipe_blocks = 0;
+        h->early_done = false; h->early_iter = -1; h->early_EW = h->early_EH = nullptr;
+        free_data(h);
+        return code;
+    };
     fill_mask_kernel<<<nblk(N * h->Fw, 256), 256, 0, h->stream>>>(h->mc, N, h->Fw, F);
-    LAUNCH_CHECK();
+    if (cudaGetLastError() != cudaSuccess) return bail(fail(h, NBMF_ERR_CUDA, "fill_mask launch failed"));
     fill_mask_kernel<<<nblk(F * h->Nw, 256), 256, 0, h->stream>>>(h->mr, F, h->Nw, N);
-    LAUNCH_CHECK();
-    if ((rc = nbmf_vb_begin(h, K, alpha, beta, gamma, 0))) { cudaStreamSynchronize(h->copy_stream); return rc; }
+    if (cudaGetLastError() != cudaSuccess) return bail(fail(h, NBMF_ERR_CUDA, "fill_mask launch failed"));
+    h->horizon_next = std::max(1, iter);
+    if ((rc = nbmf_vb_begin(h, K, alpha, beta, gamma, 0))) return bail(rc);
+    if (!use_tensor_path(h)) return bail(fail(h, NBMF_ERR_STATE, "internal: pipelined upload without the tensor path"));
     h->pipe_blocks = nb;
+    h->early_EW = E_W; h->early_EH = E_H; h->early_iter = iter - 1; h->early_done = false;
     for (int i = 0; i < iter; i++)
-        if ((rc = nbmf_vb_step(h, checklb))) {
-            h->vb_active = false; h->pipe_blocks = 0;
-            cudaStreamSynchronize(h->copy_stream);   // the host buffer must not be in use after the return
-            return rc;
-        }
+        if ((rc = nbmf_vb_step(h, checklb))) return bail(rc);
     rc = nbmf_vb_end(h, E_W, E_H, lowerbounds, iter, nullptr);
+    if (rc) return bail(rc);
     cudaStreamSynchronize(h->copy_stream);
     return rc;
 }
@@ -828,8 +1010,9 @@ extern "C" int nbmf_vb_argmax_labels(nbmf_handle *h, int32_t *Z_out)
 {
     if (!h) return NBMF_ERR_ARG;
     if (!h->A || !h->BB || h->Kc <= 0) return fail(h, NBMF_ERR_STATE, "no VB operands: run nbmf_vb_aspect / nbmf_vb_step first");
-    if (h->hook) return fail(h, NBMF_ERR_UNSUPPORTED, "argmax labels under column sharding: call per rank on its own block");
-    CK(cudaSetDevice(h->device));
+    CK(cudaSetDevice(h->device));   // under column sharding the labels are those of the handle's own block
+    CK(cudaStreamSynchronize(h->stream));
+    { int rc0 = tp_check_error(h); if (rc0) return rc0; }
     const int64_t F = h->F, N = h->N;
     if ((double)F * N * 4 > 64e9) return fail(h, NBMF_ERR_UNSUPPORTED, "label matrix too large");
     cudaFree(h->Z); h->Z = nullptr;
@@ -847,6 +1030,7 @@ extern "C" int nbmf_lower_bound(nbmf_handle *h, int K, double alpha, double beta
     if (!h) return NBMF_ERR_ARG;
     if (!h->statF || h->Kc != K) return fail(h, NBMF_ERR_STATE, "statistics missing");
     CK(cudaSetDevice(h->device));
+    resolve_path(h, K, 1);
     if (use_tensor_path(h)) { int rc0 = tp_prepare(h); if (rc0) return rc0; }
     CK(cudaMemsetAsync(h->scal, 0, 3 * sizeof(double), h->stream));
     int rc;
@@ -1000,6 +1184,7 @@ extern "C" int nbmf_vb_dirber(nbmf_handle *h, int K, double alpha, double beta, 
     // contraction form: same Kc = K+1 columns, iter-1 batch sweeps, mean parameters
     const int Kc = K + 1;
     if (h->Kc != Kc) return fail(h, NBMF_ERR_STATE, "statistics must be initialised with Kc = K+1");
+    h->horizon_next = std::max(1, iter - 1);
     int rc = nbmf_vb_begin(h, Kc, alpha, beta, gamma, 1);
     if (rc) return rc;
     for (int i = 1; i < iter; i++)
@@ -1011,15 +1196,164 @@ extern "C" int nbmf_vb_dirber(nbmf_handle *h, int K, double alpha, double beta, 
 // ---------------------------------------------------------------------------
 // Gibbs
 // ---------------------------------------------------------------------------
-extern "C" int nbmf_gibbs_dirber(nbmf_handle *h, int K, double alpha, double beta, double gamma, int iter,
-                                 double burnin, uint64_t seed, double *E_W, double *E_H,
-                                 const int64_t *test_idx, int64_t n_test, double *E_V_test, int32_t *Z_last)
+template <int KT>
+static cudaError_t launch_gibbs_sweep(const GibbsSweepArgs &a, dim3 grid, cudaStream_t st)
 {
-    if (!h) return NBMF_ERR_ARG;
-    if (!h->vc) return fail(h, NBMF_ERR_STATE, "no data");
-    if (K <= 0 || K > 256) return fail(h, NBMF_ERR_ARG, "Gibbs: K must be in 1..256");
-    if (!(alpha > 0) || !(beta > 0) || !(gamma > 0)) return fail(h, NBMF_ERR_ARG, "priors must be > 0");
-    CK(cudaSetDevice(h->device));
+    cudaError_t e = cudaFuncSetAttribute(gibbs_sweep_kt_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GibbsSmem<KT>::BYTES);
+    if (e != cudaSuccess) return e;
+    gibbs_sweep_kt_kernel<KT><<<grid, 256, GibbsSmem<KT>::BYTES, st>>>(a);
+    return cudaGetLastError();
+}
+
+// Uncollapsed blocked chain, K <= 32: two launches per sweep (gibbs_fast.cuh).  Sweep i draws W, H from
+// the counts of sweep i-1, then samples every entry; a kept sweep (i >= floor(iter * burnin), the
+// reference's bookkeeping, collapsed_gibbs_z.cpp:423-426) adds the Rao-Blackwell means of ITS counts,
+// which the next draw launch (or a final accumulation-only one) does.
+static int gibbs_dirber_fast(nbmf_handle *h, int K, double alpha, double beta, double gamma, int iter,
+                             double burnin, uint64_t seed, double *E_W, double *E_H,
+                             const int64_t *test_idx, int64_t n_test, double *E_V_test, int32_t *Z_last)
+{
+    const int64_t F = h->F, N = h->N;
+    const int KT = K <= 4 ? 4 : K <= 8 ? 8 : K <= 16 ? 16 : 32;
+    const size_t fk = (size_t)F * K, nk = (size_t)N * K, fkt = (size_t)F * KT, nkt = (size_t)N * KT;
+    const int f_tiles = (int)((F + GIBBS_FB - 1) / GIBBS_FB);
+    // column-side counts: per-row-tile partial buffers (plain stores) while they stay small, integer atomics beyond
+    const bool cn_atomic = f_tiles > 16;
+    DevBuf<int32_t> cF, cN, cNp, Zd;
+    DevBuf<float> W, HH, wc, hc;
+    DevBuf<double> accW, accH, accV, outb;
+    DevBuf<int64_t> didx;
+    CK(cF.alloc(fkt)); CK(cN.alloc(2 * nkt));
+    if (!cn_atomic) CK(cNp.alloc((size_t)f_tiles * 2 * nkt));
+    CK(W.alloc(fkt)); CK(HH.alloc(2 * nkt)); CK(wc.alloc(fk)); CK(hc.alloc(nk));
+    CK(accW.alloc(fk)); CK(accH.alloc(nk)); CK(outb.alloc(std::max(fk, nk)));
+    if (n_test > 0) { CK(accV.alloc((size_t)n_test)); CK(didx.alloc((size_t)n_test)); }
+    if (Z_last) CK(Zd.alloc((size_t)F * N));
+    unsigned long long *cnt = (unsigned long long *)h->scal + SC_TMP;
+    const int nburnin = (int)std::floor(iter * burnin);
+    h->timing = nbmf_timing{};
+    CK(cudaMemsetAsync(cF, 0, fkt * 4, h->stream)); CK(cudaMemsetAsync(cN, 0, 2 * nkt * 4, h->stream));
+    CK(cudaMemsetAsync(accW, 0, fk * 8, h->stream)); CK(cudaMemsetAsync(accH, 0, nk * 8, h->stream));
+    CK(cudaMemsetAsync(cnt, 0, 16, h->stream));
+    if (n_test > 0) {
+        CK(cudaMemsetAsync(accV, 0, (size_t)n_test * 8, h->stream));
+        CK(cudaMemcpyAsync(didx, test_idx, (size_t)n_test * 8, cudaMemcpyHostToDevice, h->stream));
+    }
+    // initial counts: from stored labels (compute_counts) when available, else from the fp64
+    // statistics (which hold integer counts after a label initialisation)
+    if (h->Z) {
+        gibbs_counts_from_labels_kernel<<<nblk(F * N, 256), 256, 0, h->stream>>>(h->Z, h->vc, h->has_na ? h->mc : nullptr, F, N, h->Fw, K, KT, cF, cN, cnt + 1);
+        LAUNCH_CHECK();
+        unsigned long long bad = 0;
+        CK(cudaMemcpyAsync(&bad, cnt + 1, 8, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        if (bad) return fail(h, NBMF_ERR_ARG, "Z contains labels outside 0..K-1 (BernoulliNMF.R:18-20 forces K_init=10)");
+        int rc = nbmf_sum_ranks(h, cF, fkt, 1, h->stream);   // row counts are over all ranks' columns
+        if (rc) return rc;
+    } else if (h->statF && h->Kc == K) {
+        gibbs_counts_from_stats_kernel<<<nblk((int64_t)std::max(fkt, 2 * nkt), 256), 256, 0, h->stream>>>(
+            h->statF, h->statN, F, N, K, h->Kp, KT, cF, cN);
+        LAUNCH_CHECK();
+    } else return fail(h, NBMF_ERR_STATE, "Gibbs needs labels: call nbmf_init_from_labels or nbmf_init_random_labels first");
+
+    GibbsDrawArgs d{};
+    d.F = F; d.N = N; d.n_offset = h->opts.n_offset; d.K = K; d.KT = KT;
+    d.alpha = alpha; d.beta = beta; d.gamma = gamma; d.seed = seed;
+    d.cF = cF; d.cN = cN; d.cNp = cNp; d.W = W; d.HH = HH; d.accW = accW; d.accH = accH; d.w_cur = wc; d.h_cur = hc;
+    GibbsSweepArgs sw{};
+    sw.vc = h->vc; sw.mc = h->has_na ? h->mc : nullptr; sw.F = F; sw.N = N; sw.Fw = h->Fw; sw.n_offset = h->opts.n_offset;
+    sw.W = W; sw.HH = HH; sw.seed = seed; sw.K = K; sw.cF = cF;
+    sw.cn_atomic = cn_atomic ? 1 : 0; sw.cNp = cn_atomic ? (int32_t *)cN : (int32_t *)cNp;
+    // enough blocks for a few waves of 148 SMs, each amortising its row histograms over ct sub-tiles
+    const int NBc = GIBBS_NB(KT);
+    const int64_t n_tiles = (N + NBc - 1) / NBc;
+    int ct = (int)std::max<int64_t>(1, std::min<int64_t>(GIBBS_CT_MAX, (n_tiles * f_tiles) / (6ll * h->sm_count)));
+    sw.ct = ct;
+    const dim3 sgrid((unsigned)((n_tiles + ct - 1) / ct), (unsigned)f_tiles);
+    const unsigned dgrid = nblk((F + N) * 32, 256);
+    int kept = 0;
+    int rc = NBMF_OK;
+    CK(cudaEventRecord(h->ev[0], h->stream));
+    bool parts_valid = false;      // cNp holds the last sweep's column-side counts
+    for (int i = 1; i < iter; i++) {
+        // counts of sweep i-1 (or the initial ones) -> means of a kept sweep, W and H of sweep i
+        d.sweep = (uint32_t)i; d.draw = 1;
+        d.accumulate = (i - 1 >= 1 && i - 1 >= nburnin) ? 1 : 0;
+        d.n_parts = (parts_valid && !cn_atomic) ? f_tiles : 0;
+        d.zero_cn = cn_atomic ? 1 : 0;
+        gibbs_draw_kernel<<<dgrid, 256, 0, h->stream>>>(d);
+        LAUNCH_CHECK();
+        if (d.accumulate) {
+            kept++;
+            if (n_test > 0) {
+                gibbs_ev_test_kernel<<<nblk(n_test, 256), 256, 0, h->stream>>>(didx, n_test, F, K, wc, hc, accV);
+                LAUNCH_CHECK();
+                h->timing.launches += 1;
+            }
+        }
+        sw.sweep = (uint32_t)i; sw.Zout = (i == iter - 1) ? (int32_t *)Zd : nullptr;
+        cudaError_t e;
+        switch (KT) {
+        case 4: e = launch_gibbs_sweep<4>(sw, sgrid, h->stream); break;
+        case 8: e = launch_gibbs_sweep<8>(sw, sgrid, h->stream); break;
+        case 16: e = launch_gibbs_sweep<16>(sw, sgrid, h->stream); break;
+        default: e = launch_gibbs_sweep<32>(sw, sgrid, h->stream); break;
+        }
+        CK(e);
+        parts_valid = true;
+        h->timing.launches += 2;
+        // column sharding: the row counts are the one thing exchanged per sweep
+        if ((rc = nbmf_sum_ranks(h, cF, fkt, 1, h->stream))) return rc;
+    }
+    // the last sweep's counts
+    if (iter > 1 && iter - 1 >= nburnin) {
+        d.sweep = (uint32_t)iter; d.draw = 0; d.accumulate = 1;
+        d.n_parts = (parts_valid && !cn_atomic) ? f_tiles : 0; d.zero_cn = 0;
+        gibbs_draw_kernel<<<dgrid, 256, 0, h->stream>>>(d);
+        LAUNCH_CHECK();
+        kept++;
+        if (n_test > 0) {
+            gibbs_ev_test_kernel<<<nblk(n_test, 256), 256, 0, h->stream>>>(didx, n_test, F, K, wc, hc, accV);
+            LAUNCH_CHECK();
+        }
+        h->timing.launches += 1 + (n_test > 0);
+    }
+    CK(cudaEventRecord(h->ev[6], h->stream));
+    if (kept == 0) {
+        // iter <= 1 or a burn-in that keeps nothing: the reference divides by zero kept samples; say so
+        CK(cudaStreamSynchronize(h->stream));
+        return fail(h, NBMF_ERR_ARG, "Gibbs: no sweep is kept (iter must be >= 2 and floor(iter*burnin) <= iter-1)");
+    }
+    const double sc = 1.0 / kept;
+    if (E_W) {
+        scale_rows_to_colmajor_kernel<<<nblk(F * K, 256), 256, 0, h->stream>>>(accW, F, K, sc, outb);
+        LAUNCH_CHECK();
+        CK(cudaMemcpyAsync(E_W, outb, fk * 8, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    if (E_H) {
+        scale_rows_to_colmajor_kernel<<<nblk(N * K, 256), 256, 0, h->stream>>>(accH, N, K, sc, outb);
+        LAUNCH_CHECK();
+        CK(cudaMemcpyAsync(E_H, outb, nk * 8, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    if (E_V_test && n_test > 0) {
+        CK(cudaMemcpyAsync(E_V_test, accV, (size_t)n_test * 8, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        for (int64_t t = 0; t < n_test; t++) E_V_test[t] *= sc;
+    }
+    if (Z_last) CK(cudaMemcpyAsync(Z_last, Zd, (size_t)F * N * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    float ms = 0; cudaEventElapsedTime(&ms, h->ev[0], h->ev[6]);
+    h->timing.total_ms = ms; h->timing.iters = iter - 1;
+    return NBMF_OK;
+}
+
+// K > 32: one 32 x 32 entry tile per block, two passes over K, shared-memory histograms
+static int gibbs_dirber_wide(nbmf_handle *h, int K, double alpha, double beta, double gamma, int iter,
+                             double burnin, uint64_t seed, double *E_W, double *E_H,
+                             const int64_t *test_idx, int64_t n_test, double *E_V_test, int32_t *Z_last)
+{
     const int64_t F = h->F, N = h->N;
     const size_t fk = (size_t)F * K, nk = (size_t)N * K;
     int32_t *cF = nullptr, *cN = nullptr, *Zd = nullptr;
@@ -1031,14 +1365,12 @@ extern "C" int nbmf_gibbs_dirber(nbmf_handle *h, int K, double alpha, double bet
     A1((void **)&cF, fk * 4); A1((void **)&cN, 2 * nk * 4);
     A1((void **)&W, fk * 4); A1((void **)&H, nk * 4); A1((void **)&wc, fk * 4); A1((void **)&hc, nk * 4);
     A1((void **)&accW, fk * 8); A1((void **)&accH, nk * 8); A1((void **)&outb, std::max(fk, nk) * 8);
-    // column sharding: the row counts n_total (F x K) are the one thing exchanged per sweep; the
-    // hook sums fp64, so the int32 counts take a round trip through `outb`
+    // column sharding: the row counts n_total (F x K) are the one thing exchanged per sweep.  A
+    // failed exchange ends the chain: carrying on with rank-local counts would return wrong means.
+    int xrc = NBMF_OK;
     auto exchange_counts = [&]() -> cudaError_t {
-        if (!h->hook) return cudaSuccess;
-        i32_to_f64_kernel<<<nblk((int64_t)fk, 256), 256, 0, h->stream>>>(cF, (int64_t)fk, outb);
-        if (h->hook(h->hook_ctx, (void *)outb, fk, (void *)h->stream) != 0) return cudaErrorUnknown;
-        f64_to_i32_kernel<<<nblk((int64_t)fk, 256), 256, 0, h->stream>>>(outb, (int64_t)fk, cF);
-        return cudaGetLastError();
+        xrc = nbmf_sum_ranks(h, cF, fk, 1, h->stream);
+        return xrc == NBMF_OK ? cudaGetLastError() : cudaErrorUnknown;
     };
     if (n_test > 0) { A1((void **)&accV, (size_t)n_test * 8); A1((void **)&didx, (size_t)n_test * 8); }
     if (Z_last) A1((void **)&Zd, (size_t)F * N * 4);
@@ -1090,7 +1422,9 @@ extern "C" int nbmf_gibbs_dirber(nbmf_handle *h, int K, double alpha, double bet
             cudaMemsetAsync(cN, 0, 2 * nk * 4, h->stream);
             gibbs_sweep_kernel<<<sgrid, 256, smem_sweep, h->stream>>>(h->vc, h->has_na ? h->mc : nullptr, F, N, h->Fw, h->opts.n_offset, K, W, H, seed, (uint32_t)i, cF, cN, (i == iter - 1) ? Zd : nullptr);
             h->timing.launches += 5;
+            e = cudaGetLastError();
             if (e == cudaSuccess) e = exchange_counts();
+            if (e != cudaSuccess) break;
             if (i >= nburnin) {
                 gibbs_accumulate_kernel<<<nblk(std::max(F, N), 256), 256, 0, h->stream>>>(cF, cN, F, N, K, alpha, beta, gamma, accW, accH, wc, hc);
                 if (n_test > 0)
@@ -1129,8 +1463,26 @@ extern "C" int nbmf_gibbs_dirber(nbmf_handle *h, int K, double alpha, double bet
     }
     cudaFree(cF); cudaFree(cN); cudaFree(W); cudaFree(H); cudaFree(wc); cudaFree(hc);
     cudaFree(accW); cudaFree(accH); cudaFree(accV); cudaFree(outb); cudaFree(didx); cudaFree(Zd);
+    if (xrc != NBMF_OK) return xrc;   // h->err holds the collective's message
     if (e != cudaSuccess) { h->err = std::string("gibbs: ") + cudaGetErrorString(e); cudaGetLastError(); return NBMF_ERR_CUDA; }
     return rc;
+}
+
+extern "C" int nbmf_gibbs_dirber(nbmf_handle *h, int K, double alpha, double beta, double gamma, int iter,
+                                 double burnin, uint64_t seed, double *E_W, double *E_H,
+                                 const int64_t *test_idx, int64_t n_test, double *E_V_test, int32_t *Z_last)
+{
+    if (!h) return NBMF_ERR_ARG;
+    if (!h->vc) return fail(h, NBMF_ERR_STATE, "no data");
+    if (K <= 0 || K > 256) return fail(h, NBMF_ERR_ARG, "Gibbs: K must be in 1..256");
+    if (!(alpha > 0) || !(beta > 0) || !(gamma > 0)) return fail(h, NBMF_ERR_ARG, "priors must be > 0");
+    if (iter < 2 || !(burnin >= 0) || std::floor(iter * burnin) > iter - 1)
+        return fail(h, NBMF_ERR_ARG, "Gibbs: no sweep is kept (iter must be >= 2 and floor(iter*burnin) <= iter-1)");
+    CK(cudaSetDevice(h->device));
+    static const bool force_wide = [] { const char *v = getenv("NBMF_GIBBS_KERNEL"); return v && strcmp(v, "wide") == 0; }();
+    if (K <= 32 && !force_wide)
+        return gibbs_dirber_fast(h, K, alpha, beta, gamma, iter, burnin, seed, E_W, E_H, test_idx, n_test, E_V_test, Z_last);
+    return gibbs_dirber_wide(h, K, alpha, beta, gamma, iter, burnin, seed, E_W, E_H, test_idx, n_test, E_V_test, Z_last);
 }
 
 // The reference's collapsed samplers with their own schedule: the sequential sweep in anti-diagonal
@@ -1308,3 +1660,5 @@ extern "C" int nbmf_predictive_ll(nbmf_handle *h, const double *E_W, const doubl
     if (n_test) { unsigned long long c; memcpy(&c, &out[1], 8); *n_test = (int64_t)c; }
     return NBMF_OK;
 }
+
+#include "nbmf_extra.cuh"

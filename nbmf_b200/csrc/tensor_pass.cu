@@ -37,7 +37,9 @@
 #include <cstdlib>
 
 #define TP_THREADS 640
-#define TP_SPIN_LIMIT (1u << 20)
+// failed barrier probes before a role gives up and raises the abort flag (about 0.1 s at the
+// default; a debugger, compute-sanitizer or a heavy ncu replay may need more: NBMF_TP_SPIN_LIMIT)
+__constant__ uint32_t c_tp_spin_limit = 1u << 20;
 
 // ---------------------------------------------------------------------------
 // host-side state
@@ -77,12 +79,72 @@ static PFN_encodeTiled get_encode()
     return fn;
 }
 
-bool tp_supported(const nbmf_handle *h)
+bool tp_supported(const nbmf_handle *h, int K)
 {
     if (h->cc_major != 10) return false;
-    if (h->Kc <= 32 || h->Kc > 128) return false;
+    if (K <= 32 || K > 128) return false;
     if (h->F < 256 || h->N < 256) return false;
     return true;
+}
+
+// ---------------------------------------------------------------------------
+// AUTO precision.  The relative Frobenius error of E_W / E_H against the FP64 path after `it` VB
+// updates from a random start is modelled as
+//     err(variant, n, it) = rnd_variant(it) * sqrt(4096 / n) + sys_variant(it),   n = min(F, N_global)
+// rnd = the part made of per-entry independent roundings (R to f16, the streamed operand's hi part),
+// which averages out over the reduction; sys = the owner operand's f16 rounding in stage 1, fixed
+// per lane for a whole pass, which does not (only the ACC variant removes it).  The tables are the
+// measured curves of profiles/r2_error_growth_*.log (K = 128, gamma = 1/K, the worse of E_W / E_H),
+// log-interpolated in `it`; tools/error_growth.py regenerates them.  AUTO takes the cheapest variant
+// whose modelled error is below 0.7e-5, and the FP64 path if none is.
+// ---------------------------------------------------------------------------
+static const int kErrIts[] = {1, 2, 5, 10, 20, 40, 60, 80, 100, 200};
+static const double kErrRnd[3][10] = {
+    // FAST (hi only)
+    {3.3e-6, 4.9e-6, 7.8e-6, 1.2e-5, 2.0e-5, 3.9e-5, 7.7e-5, 1.4e-4, 2.0e-4, 6.0e-4},
+    // TENSOR (stage 2 hi+lo)
+    {5.8e-7, 8.1e-7, 1.6e-6, 2.6e-6, 3.9e-6, 6.5e-6, 1.0e-5, 1.6e-5, 2.3e-5, 7.0e-5},
+    // ACC (stage 1 and 2 hi+lo)
+    {5.8e-7, 8.1e-7, 1.6e-6, 2.6e-6, 3.9e-6, 6.0e-6, 9.0e-6, 1.3e-5, 1.9e-5, 6.0e-5},
+};
+static const double kErrSys[3][10] = {
+    {3e-7, 5e-7, 1.2e-6, 2.0e-6, 3.3e-6, 6.5e-6, 1.0e-5, 1.5e-5, 2.0e-5, 5e-5},
+    {3e-7, 5e-7, 1.2e-6, 2.0e-6, 3.3e-6, 6.5e-6, 1.0e-5, 1.5e-5, 2.0e-5, 5e-5},
+    {0, 0, 0, 0, 0, 0, 0, 0, 0, 0},
+};
+
+static double tp_model_error(int variant /*0 FAST, 1 TENSOR, 2 ACC*/, double n, int it)
+{
+    const int NI = (int)(sizeof(kErrIts) / sizeof(kErrIts[0]));
+    it = std::max(1, it);
+    int j = 0;
+    while (j + 1 < NI && kErrIts[j + 1] <= it) j++;
+    auto at = [&](const double *tab) {
+        if (j + 1 >= NI) return tab[NI - 1] * (double)it / kErrIts[NI - 1];        // beyond the table: linear growth
+        const double t = (std::log((double)it) - std::log((double)kErrIts[j])) /
+                         (std::log((double)kErrIts[j + 1]) - std::log((double)kErrIts[j]));
+        return tab[j] + t * (tab[j + 1] - tab[j]);
+    };
+    return at(kErrRnd[variant]) * std::sqrt(4096.0 / n) + at(kErrSys[variant]);
+}
+
+int tp_auto_mode(const nbmf_handle *h, int K, int horizon)
+{
+    if (!tp_supported(h, K)) return NBMF_PATH_FP64;
+    const int64_t n_glob = h->opts.n_global > 0 ? h->opts.n_global : h->N;
+    const double n = (double)std::min<int64_t>(h->F, n_glob);
+    const double gate = 0.7e-5;
+    if (tp_model_error(0, n, horizon) < gate) return NBMF_PATH_TENSOR_FAST;
+    if (tp_model_error(1, n, horizon) < gate) return NBMF_PATH_TENSOR;
+    if (tp_model_error(2, n, horizon) < gate) return NBMF_PATH_TENSOR_ACC;
+    return NBMF_PATH_FP64;
+}
+
+// modelled error of a variant, for tools and tests (not part of the public header)
+extern "C" double nbmf_debug_model_error(int path, double n, int iters)
+{
+    const int v = path == NBMF_PATH_TENSOR_FAST ? 0 : path == NBMF_PATH_TENSOR ? 1 : path == NBMF_PATH_TENSOR_ACC ? 2 : -1;
+    return v < 0 ? 0.0 : tp_model_error(v, n, iters);
 }
 
 void tp_invalidate_data(nbmf_handle *h)
@@ -156,6 +218,10 @@ int tp_prepare(nbmf_handle *h)
     if (rc) return rc;
     rc = make_map(h, &s->tmBlo, s->B_lo, s->N2pad, KP);
     if (rc) return rc;
+    if (const char *sl = getenv("NBMF_TP_SPIN_LIMIT")) {
+        const long long v = atoll(sl);
+        if (v > 1024) { uint32_t lim = (uint32_t)std::min<long long>(v, 0xffffffffll); cudaMemcpyToSymbol(c_tp_spin_limit, &lim, 4); }
+    }
     s->chunk_steps = h->opts.flush_interval > 0 ? h->opts.flush_interval : 512;
     const char *env = getenv("NBMF_TP_CHUNK_STEPS");
     if (env && atoi(env) > 0) s->chunk_steps = atoi(env);
@@ -260,14 +326,15 @@ __global__ void tp_finalize_kernel(const double *__restrict__ U, const double *_
 // First-order ELBO correction for the single-f16 stage 1:
 //   sum log D  ~=  sum log D_hi + sum_lk (U - U_hi)_lk G_lk     over both passes' owners,
 // because D - D_hi = (U-U_hi).W_hi + U_hi.(W-W_hi) + O(2^-24) and sum_c R_lc W_c = G_l.
-__global__ void tp_logcorr_kernel(const double *__restrict__ U, const __half *__restrict__ Uhi, const double *__restrict__ G,
-                                  int64_t count, const int *dexp, int which, double *sumlogD)
+__global__ void tp_logcorr_kernel(const double *__restrict__ U, const __half *__restrict__ Uhi, const __half *__restrict__ Ulo,
+                                  const double *__restrict__ G, int64_t count, const int *dexp, int which, double *sumlogD)
 {
     __shared__ double sh[32];
     const double inv = ldexp(1.0, -dexp[which]);
     double t = 0.0;
+    // Ulo != NULL: stage 1 of the pass that accumulated the logarithms already used U_hi + U_lo
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
-        t += (U[i] - (double)__half2float(Uhi[i]) * inv) * G[i];
+        t += (U[i] - ((double)__half2float(Uhi[i]) + (Ulo ? (double)__half2float(Ulo[i]) : 0.0)) * inv) * G[i];
     t = block_sum(t, sh);
     if (threadIdx.x == 0) atomicAdd(sumlogD, t);
 }
@@ -278,8 +345,11 @@ int tp_log_correction(nbmf_handle *h, int owner_rows, double *sumlogD)
     if (!s || !sumlogD) return NBMF_OK;
     const int64_t cnt = (owner_rows ? h->F : 2 * h->N) * (int64_t)s->KP;
     tp_logcorr_kernel<<<(unsigned)std::min<int64_t>(2048, (cnt + 255) / 256), 256, 0, h->stream>>>(
-        owner_rows ? h->A : h->BB, owner_rows ? s->A_hi : s->B_hi, owner_rows ? h->GF : h->GN, cnt, s->dexp,
-        owner_rows ? 0 : 1, sumlogD);
+        owner_rows ? h->A : h->BB, owner_rows ? s->A_hi : s->B_hi,
+        // the logarithms come from the rows pass: its owner (A) carries the lo part in ACC mode, its
+        // streamed operand (B) never does
+        (owner_rows && h->path_mode == NBMF_PATH_TENSOR_ACC) ? s->A_lo : nullptr,
+        owner_rows ? h->GF : h->GN, cnt, s->dexp, owner_rows ? 0 : 1, sumlogD);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { h->err = std::string("tp_log_correction: ") + cudaGetErrorString(e); return NBMF_ERR_CUDA; }
     h->timing.launches += 1;
@@ -365,7 +435,7 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, volatil
 {
     if (mbar_try(bar, parity)) return true;
 #pragma unroll 1
-    for (uint32_t spin = 1; spin < TP_SPIN_LIMIT; spin++) {
+    for (uint32_t spin = 1, lim = c_tp_spin_limit; spin < lim; spin++) {
         if (mbar_try(bar, parity)) return true;
         if ((spin & 1023u) == 0u && *abort_flag) return false;
     }
@@ -508,6 +578,8 @@ struct TPArgs {
     float *dbg;                    // optional debug dump
     int dbg_flags;                 // timing experiments only: 1 = skip lo TMA, 2 = skip all TMA
     int use_lo;                    // stage 2 adds the W_lo term (NBMF_PREC_TENSOR); 0 = hi only (NBMF_PREC_TENSOR_FAST)
+    const __half *U_lo;            // owner operand lo part, rows [Lpad][KP] (NBMF_PREC_TENSOR_ACC: stage 1 adds U_lo . W_hi)
+    int use_ulo;
 };
 
 // One step = 64 streamed rows.  Shared-memory stage: [hi: KB blocks]([lo: KB blocks] when the
@@ -524,7 +596,7 @@ struct TPArgs {
 // return even when the phase completed long ago, and arrive -> wake-up of a blocked waiter
 // ~180.  Both issuers therefore start the try_wait of step t+1 BEFORE they issue the MMAs of
 // step t and only fall back to a blocking wait when that early probe failed.
-template <int KP, bool USE_LO>
+template <int KP, bool USE_LO, bool USE_ULO>
 struct TPCfg {
     static constexpr int KB = KP / 64;
     static constexpr int STEP_ROWS = 64;
@@ -532,22 +604,26 @@ struct TPCfg {
     static constexpr int PART_BYTES = KB * BLOCK_BYTES;     // hi (or lo) part of a stage
     static constexpr int TILE_BYTES = (USE_LO ? 2 : 1) * PART_BYTES;
     static constexpr int STAGES = (224 * 1024 / TILE_BYTES) > 16 ? 16 : (224 * 1024 / TILE_BYTES);
-    static constexpr int NS = 3;                            // S slots (fp32 stage-1 accumulators, 64 columns each)
+    // S slots (fp32 stage-1 accumulators, 64 columns each).  With the owner's lo part in TMEM as well
+    // (USE_ULO) KP = 128 leaves room for two; stage 1 then takes twice as long, so two are enough.
+    static constexpr int NS = (USE_ULO && KP == 128) ? 2 : 3;
     static constexpr int NR = 4;                            // R slots (f16 reciprocals, 32 columns each)
     static constexpr int COL_G = 0;
     static constexpr int COL_S = KP;                        // + 64 * (step % NS)
     static constexpr int COL_R = KP + 64 * NS;              // + 32 * (step % NR)
     static constexpr int COL_U = COL_R + 32 * NR;           // KP/2 columns; KP = 128: 448 + 64 = 512
+    static constexpr int COL_ULO = COL_U + KP / 2;          // KP/2 columns (USE_ULO only; KP = 128: 384 + 64 + 64 = 512)
+    static_assert(COL_U + (USE_ULO ? KP : KP / 2) <= 512, "TMEM columns");
     static constexpr int SMEM_BYTES = STAGES * TILE_BYTES + 1024 /*align*/ + 512 /*barriers*/;
     static_assert(2 * STAGES + NS + 3 * NR + 2 + 8 <= 64, "barrier area");
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory");
 };
 
-template <int KP, bool ROWS, bool WANT_LOG, bool HAS_NA, bool USE_LO>
+template <int KP, bool ROWS, bool WANT_LOG, bool HAS_NA, bool USE_LO, bool USE_ULO>
 __global__ void __launch_bounds__(TP_THREADS, 1)
 tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__ CUtensorMap tmLo, TPArgs a)
 {
-    using C = TPCfg<KP, USE_LO>;
+    using C = TPCfg<KP, USE_LO, USE_ULO>;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = smem_base + C::STAGES * C::TILE_BYTES;
@@ -693,6 +769,13 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
                     for (int kk = 0; kk < KP / 16; kk++)
                         tc_mma_ts2(d, tmem + C::COL_U + kk * 8,
                                    lo + (((kk >> 2) * C::BLOCK_BYTES + (kk & 3) * 32) >> 4), DHI, IDESC1, kk ? 1u : 0u);
+                    if (USE_ULO) {   // S += U_lo . W_hi^T: removes the owner's rounding error, the one that does not
+                                     // average out over the reduction (tools/numerics_study.py)
+#pragma unroll
+                        for (int kk = 0; kk < KP / 16; kk++)
+                            tc_mma_ts2(d, tmem + C::COL_ULO + kk * 8,
+                                       lo + (((kk >> 2) * C::BLOCK_BYTES + (kk & 3) * 32) >> 4), DHI, IDESC1, 1u);
+                    }
                     PROF_ACC(3);
                     tc_commit(sfull);
                     PROF_ACC(4);
@@ -799,13 +882,21 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
             const bool lane_ok = l < a.L;
             // ---- owner operand of this item: issue the global loads before waiting for the
             //      previous item's accumulator, so their latency overlaps its last MMAs
-            uint32_t ur[16];
+            uint32_t ur[16], ul[16];
             if (grp < KP / 32) {
                 const __half *src = a.U_hi + l * KP + grp * 32;
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
                     uint4 v = lane_ok ? __ldg(reinterpret_cast<const uint4 *>(src) + i) : make_uint4(0, 0, 0, 0);
                     ur[4 * i] = v.x; ur[4 * i + 1] = v.y; ur[4 * i + 2] = v.z; ur[4 * i + 3] = v.w;
+                }
+                if (USE_ULO) {
+                    const __half *srl = a.U_lo + l * KP + grp * 32;
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        uint4 v = lane_ok ? __ldg(reinterpret_cast<const uint4 *>(srl) + i) : make_uint4(0, 0, 0, 0);
+                        ul[4 * i] = v.x; ul[4 * i + 1] = v.y; ul[4 * i + 2] = v.z; ul[4 * i + 3] = v.w;
+                    }
                 }
             }
             // ---- drain G of the previous item
@@ -817,6 +908,7 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
             }
             if (grp < KP / 32) {
                 tc_st16(tmem + lane_addr + C::COL_U + grp * 16, ur);
+                if constexpr (USE_ULO) tc_st16(tmem + lane_addr + C::COL_ULO + grp * 16, ul);
                 tc_wait_st();
             }
             tc_fence_before();
@@ -854,7 +946,7 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
                 }
                 if (t + 4 < nst) load_bits();
                 const uint32_t gs = base + (uint32_t)t;
-                const uint32_t s_use = gs / 3u, sslot = gs - 3u * s_use;
+                const uint32_t sslot = gs % (uint32_t)C::NS;
                 const uint32_t t_s = tmem + lane_addr + C::COL_S + 64 * sslot;
                 // one half (32 S columns) of the step: select, shared reciprocal, pack to f16
                 auto half_step = [&](const int cc, const uint32_t (&s)[32], uint32_t (&rp)[16]) {
@@ -974,21 +1066,28 @@ __global__ void tp_logfix_kernel(const double *dacc, const int *dexp, double nse
         *sumlogD += 0.6931471805599453 * dacc[0];
 }
 
-template <int KP, bool ROWS, bool WANT_LOG, bool HAS_NA, bool USE_LO>
+template <int KP, bool ROWS, bool WANT_LOG, bool HAS_NA, bool USE_LO, bool USE_ULO>
 static cudaError_t launch_tp3(const CUtensorMap &tm, const CUtensorMap &tmlo, const TPArgs &a, int grid, cudaStream_t st)
 {
-    auto kern = tp_pass_kernel<KP, ROWS, WANT_LOG, HAS_NA, USE_LO>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TPCfg<KP, USE_LO>::SMEM_BYTES);
+    auto kern = tp_pass_kernel<KP, ROWS, WANT_LOG, HAS_NA, USE_LO, USE_ULO>;
+    using C = TPCfg<KP, USE_LO, USE_ULO>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) return e;
-    kern<<<grid, TP_THREADS, TPCfg<KP, USE_LO>::SMEM_BYTES, st>>>(tm, tmlo, a);
+    kern<<<grid, TP_THREADS, C::SMEM_BYTES, st>>>(tm, tmlo, a);
     return cudaGetLastError();
+}
+// three precision variants: hi only (FAST), + W_lo in stage 2 (TENSOR), + U_lo in stage 1 (ACC)
+template <int KP, bool ROWS, bool WANT_LOG, bool HAS_NA>
+static cudaError_t launch_tp2(const CUtensorMap &tm, const CUtensorMap &tmlo, const TPArgs &a, int grid, cudaStream_t st)
+{
+    if (a.use_ulo) return launch_tp3<KP, ROWS, WANT_LOG, HAS_NA, true, true>(tm, tmlo, a, grid, st);
+    if (a.use_lo) return launch_tp3<KP, ROWS, WANT_LOG, HAS_NA, true, false>(tm, tmlo, a, grid, st);
+    return launch_tp3<KP, ROWS, WANT_LOG, HAS_NA, false, false>(tm, tmlo, a, grid, st);
 }
 template <int KP, bool ROWS, bool WANT_LOG>
 static cudaError_t launch_tp(const CUtensorMap &tm, const CUtensorMap &tmlo, const TPArgs &a, int grid, cudaStream_t st, bool has_na)
 {
-    if (a.use_lo)
-        return has_na ? launch_tp3<KP, ROWS, WANT_LOG, true, true>(tm, tmlo, a, grid, st) : launch_tp3<KP, ROWS, WANT_LOG, false, true>(tm, tmlo, a, grid, st);
-    return has_na ? launch_tp3<KP, ROWS, WANT_LOG, true, false>(tm, tmlo, a, grid, st) : launch_tp3<KP, ROWS, WANT_LOG, false, false>(tm, tmlo, a, grid, st);
+    return has_na ? launch_tp2<KP, ROWS, WANT_LOG, true>(tm, tmlo, a, grid, st) : launch_tp2<KP, ROWS, WANT_LOG, false>(tm, tmlo, a, grid, st);
 }
 
 static float *g_tp_dbg = nullptr; // set by nbmf_debug_tp_dump only
@@ -1008,24 +1107,19 @@ static void tp_base_args(nbmf_handle *h, TPState *s, int owner_rows, bool want_l
 {
     int64_t S_rows;
     if (owner_rows) {
-        a.U_hi = s->A_hi; a.vbits = h->vr; a.mbits = h->mr; a.words = h->Nw;
+        a.U_hi = s->A_hi; a.U_lo = s->A_lo; a.vbits = h->vr; a.mbits = h->mr; a.words = h->Nw;
         a.L = h->F; S_rows = 2 * h->N;
     } else {
-        a.U_hi = s->B_hi; a.vbits = h->vc; a.mbits = h->mc; a.words = h->Fw;
+        a.U_hi = s->B_hi; a.U_lo = s->B_lo; a.vbits = h->vc; a.mbits = h->mc; a.words = h->Fw;
         a.L = 2 * h->N; S_rows = h->F;
     }
     a.owner_tiles_total = (a.L + 127) / 128;
     stream_steps = (S_rows + 63) / 64;
     a.dexp = s->dexp; a.dacc = s->dacc; a.derr = s->derr; a.item_ctr = s->item_ctr;
     a.want_log = want_log;
-    // AUTO: the W_lo term of stage 2 buys ~5x accuracy at 10^3..10^4 rows/columns, but its benefit
-    // falls like 1/sqrt(reduction length): at 262144^2 hi-only is within 1.6x of hi+lo and both are
-    // ~1e-6 of the FP64 path (profiles/r1_error_growth_c5.log), so it is dropped there.
-    const int64_t n_glob = h->opts.n_global > 0 ? h->opts.n_global : h->N;
-    if (h->opts.precision == NBMF_PREC_TENSOR) a.use_lo = 1;
-    else if (h->opts.precision == NBMF_PREC_TENSOR_FAST) a.use_lo = 0;
-    else a.use_lo = (std::min<int64_t>(h->F, n_glob) < 131072) ? 1 : 0;
-    h->timing.path = a.use_lo ? 1 : 2;
+    // the precision variant was fixed for the session by nbmf_resolve_path (tp_auto_mode under AUTO)
+    a.use_lo = (h->path_mode == NBMF_PATH_TENSOR || h->path_mode == NBMF_PATH_TENSOR_ACC) ? 1 : 0;
+    a.use_ulo = (h->path_mode == NBMF_PATH_TENSOR_ACC) ? 1 : 0;
     a.dbg = g_tp_dbg;
     { const char *f = getenv("NBMF_TP_DEBUG_FLAGS"); a.dbg_flags = f ? atoi(f) : 0; }
 }

@@ -3,7 +3,10 @@
 #pragma once
 #include "common.cuh"
 
-bool tp_supported(const nbmf_handle *h);      // K, sizes and device fit the tensor path
+bool tp_supported(const nbmf_handle *h, int K);   // K, sizes and device fit the tensor path
+// AUTO precision: the fastest nbmf_path whose error growth stays inside the 1e-5 gate for `horizon`
+// updates at this size (NBMF_PATH_FP64 if no tensor variant does)
+int tp_auto_mode(const nbmf_handle *h, int K, int horizon);
 int tp_prepare(nbmf_handle *h);               // allocate f16 operand buffers + tensor maps
 int tp_convert_operands(nbmf_handle *h);      // A, BB (fp64) -> scaled f16 hi/lo
 int tp_pass(nbmf_handle *h, int owner_rows, double *sumlogD);
