@@ -37,6 +37,9 @@ WORKLOADS = {
     "c1": dict(F=200, N=300, K=3, Kt=3, gamma=1.0, a=0.1, b=0.1, seed=1,
                desc="VB_aspect, synthetic DirBer 200x300, K=3 (BASELINE configs[0] shape)"),
 }
+DTYPES = {0: "f64", 1: "f16 (streamed operand hi+lo in stage 2) / f32 accumulate in TMEM",
+          2: "f16 (hi only) / f32 accumulate in TMEM",
+          3: "f16 (owner hi+lo in stage 1, streamed hi+lo in stage 2) / f32 accumulate in TMEM", 4: "f32"}
 METRIC = "vb_entries_K_per_s"
 UNIT = "entries*K/s"
 
@@ -153,7 +156,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("NBMF_BENCH_WORKLOAD", "c5"), choices=list(WORKLOADS))
-    ap.add_argument("--precision", type=int, default=0, help="nbmf_precision (0 auto, 1 fp64, 2 tensor, 3 tensor-full)")
+    ap.add_argument("--precision", type=int, default=0, help="nbmf_precision (0 auto, 1 fp64, 2 tensor hi+lo, 3 tensor hi only, 4 tensor acc, 5 fp32)")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -277,8 +280,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "iters_per_s": args.steps / (ms * 1e-3),
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                "dtype": {0: "f64", 1: "f16 (streamed operand hi+lo in stage 2) / f32 accumulate in TMEM",
-                          2: "f16 (hi only; validated at this size, profiles/r1_error_growth_c5.log) / f32 accumulate in TMEM"}[int(tim["path"])],
+                "dtype": DTYPES[int(tim["path"])],
                 "data": "synthetic",
                 "config": {"workload": wl["desc"], "F": F, "N": N, "K": K, "columns_per_rank": Nl,
                            "step": "one VB_aspect iteration: parameters, both statistics, ELBO (checklb=TRUE)",

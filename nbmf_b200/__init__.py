@@ -7,14 +7,14 @@ kernels; there is no CPU fallback.
 """
 from . import _lib  # noqa: F401
 from .api import (  # noqa: F401
-    BernoulliNMF, Engine, Gibbs_DirBer, Gibbs_DirBer_DP, Gibbs_DirBer_DP_Rcpp, Gibbs_DirBer_finite_Rcpp, Gibbs_DirDir,
+    BernoulliNMF, Engine, Group, Gibbs_DirBer, Gibbs_DirBer_DP, Gibbs_DirBer_DP_Rcpp, Gibbs_DirBer_finite_Rcpp, Gibbs_DirDir,
     Gibbs_DirDir_finite_Rcpp,
     NA_INTEGER, NbmfError, VB_Aspect_Rcpp,
     VB_DirBer, VB_DirBer_Rcpp, VB_aspectRcpp, as_imat, expectation, loglikelihood, lower_bound_aspect,
 )
 
 __all__ = [
-    "BernoulliNMF", "Engine", "Gibbs_DirBer", "Gibbs_DirBer_DP", "Gibbs_DirBer_DP_Rcpp", "Gibbs_DirBer_finite_Rcpp",
+    "BernoulliNMF", "Engine", "Group", "Gibbs_DirBer", "Gibbs_DirBer_DP", "Gibbs_DirBer_DP_Rcpp", "Gibbs_DirBer_finite_Rcpp",
     "Gibbs_DirDir", "Gibbs_DirDir_finite_Rcpp", "NA_INTEGER", "NbmfError",
     "VB_Aspect_Rcpp", "VB_DirBer", "VB_DirBer_Rcpp", "VB_aspectRcpp", "as_imat", "expectation",
     "loglikelihood", "lower_bound_aspect",

@@ -129,6 +129,21 @@ class NbmfError(RuntimeError):
         self.code = code
 
 
+def _preload_nccl():
+    """libnbmf_cuda needs libnccl.so.2.  A process that also runs torch.distributed must end up with ONE
+    copy of NCCL: load the wheel's libnccl (the one torch uses) first when it is there, so that the
+    library's dependency resolves to it by SONAME; otherwise the system libnccl serves."""
+    import sys
+    for sp in sys.path:
+        cand = os.path.join(sp, "nvidia", "nccl", "lib", "libnccl.so.2")
+        if os.path.exists(cand):
+            try:
+                C.CDLL(cand, mode=C.RTLD_GLOBAL)
+            except OSError:
+                pass
+            return
+
+
 def load():
     """Load libnbmf_cuda.so and bind every declared symbol.  Raises if the
     library has not been built -- there is no Python / CPU fallback."""
@@ -139,6 +154,7 @@ def load():
         raise ImportError(
             f"{SO_PATH} not found: build it with `make -C nbmf_b200/csrc` "
             "(nvcc -gencode arch=compute_100a,code=sm_100a). There is no CPU fallback.")
+    _preload_nccl()
     lib = C.CDLL(SO_PATH)
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)  # AttributeError if the .so does not export it

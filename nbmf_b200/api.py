@@ -51,10 +51,10 @@ class Engine:
     """One libnbmf_cuda handle = one GPU's share of V (all of it unless sharded)."""
 
     def __init__(self, device: int = 0, precision: int = _lib.PREC_AUTO, flush_interval: int = 0,
-                 n_global: int = 0, n_offset: int = 0, pipe_block_cols: int = 0):
+                 n_global: int = 0, n_offset: int = 0, pipe_block_cols: int = 0, planned_iters: int = 0):
         self.lib = _lib.load()
         self.h = C.c_void_p()
-        opts = NbmfOpts(device, precision, flush_interval, pipe_block_cols, n_global, n_offset)
+        opts = NbmfOpts(device, precision, flush_interval, pipe_block_cols, n_global, n_offset, planned_iters, 0)
         rc = self.lib.nbmf_create(C.byref(self.h), C.byref(opts))
         if rc != 0:
             raise NbmfError(rc, "nbmf_create failed (no CUDA device? there is no CPU fallback)")
@@ -107,6 +107,28 @@ class Engine:
 
         self._hook_ref = _lib.ALLREDUCE_FN(tramp)
         self._ck(self.lib.nbmf_set_allreduce_hook(self.h, self._hook_ref, None))
+
+    # -- collectives owned by the library (one process per GPU) ----------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """128 bytes rank 0 ships to the other ranks (nbmf_comm_unique_id)."""
+        buf = C.create_string_buffer(128)
+        rc = _lib.load().nbmf_comm_unique_id(buf)
+        if rc != 0:
+            raise NbmfError(rc, "nbmf_comm_unique_id failed")
+        return buf.raw
+
+    def comm_init(self, id128: bytes, world: int, rank: int):
+        buf = C.create_string_buffer(bytes(id128), 128)
+        self._ck(self.lib.nbmf_comm_init_rank(self.h, buf, world, rank))
+
+    def comm_destroy(self):
+        self._ck(self.lib.nbmf_comm_destroy(self.h))
+
+    def comm_info(self):
+        r, w = C.c_int(0), C.c_int(1)
+        self._ck(self.lib.nbmf_comm_info(self.h, C.byref(r), C.byref(w)))
+        return r.value, w.value
 
     # -- data ------------------------------------------------------------
     def set_data(self, V):
@@ -295,6 +317,77 @@ class Engine:
                                                    burnin, seed, _ptr(Cm, _dp)))
         return Cm
 
+    def sample_gibbs_cpp(self, v_n, W, Cinit, alpha=1.0, iter=100, burnin=0.5, seed=1, as_coded=True):
+        """sample_gibbs_cpp (sample_gibbs.cpp:22-80); as_coded=False stores the draw (R sample_gibbs_Z)."""
+        v = np.ascontiguousarray(v_n, dtype=np.int32)
+        W = np.asfortranarray(W, dtype=np.float64)
+        Ci = np.asfortranarray(Cinit, dtype=np.int32)
+        F, K = W.shape
+        assert Ci.shape == (F, K) and v.shape == (F,)
+        Cm = np.zeros((F, K), order="F")
+        self._ck(self.lib.nbmf_sample_gibbs_cpp(self.h, _ptr(v, _ip), _ptr(W, _dp), _ptr(Ci, _ip), F, K, alpha, iter,
+                                                burnin, seed, int(as_coded), _ptr(Cm, _dp)))
+        return Cm
+
+    # -- posterior-mean reducers / conditional draws of the collapsed samplers ----
+    def compute_expectation_W(self, Z_samples, gamma, Kq=None):
+        Zs = np.asfortranarray(Z_samples, dtype=np.int32)
+        F, N, J = Zs.shape
+        if Kq is None:
+            Kq = int(Zs.max()) + 1           # Z_samples.max() + 1 (collapsed_gibbs_z.cpp:180)
+        E = np.zeros((F, Kq), order="F")
+        self._ck(self.lib.nbmf_compute_expectation_W(self.h, _ptr(Zs, _ip), F, N, J, gamma, Kq, _ptr(E, _dp)))
+        return E
+
+    def compute_expectation_H(self, Z_samples, V, alpha, beta, Kq=None):
+        Zs = np.asfortranarray(Z_samples, dtype=np.int32)
+        Vi = as_imat(V)
+        F, N, J = Zs.shape
+        if Kq is None:
+            Kq = int(Zs.max()) + 1
+        E = np.zeros((N, Kq), order="F")
+        self._ck(self.lib.nbmf_compute_expectation_H(self.h, _ptr(Zs, _ip), _ptr(Vi, _ip), F, N, J, alpha, beta, Kq,
+                                                     _ptr(E, _dp)))
+        return E
+
+    def samples_VWH_DirBer(self, V, Z_samples, K, gamma, alpha, beta, seed=1, want_V=True):
+        Zs = np.asfortranarray(Z_samples, dtype=np.int32)
+        Vi = as_imat(V)
+        F, N, J = Zs.shape
+        Ws = np.zeros((F, K, J), order="F"); Hs = np.zeros((N, K, J), order="F")
+        Vs = np.zeros((F, N, J), dtype=np.int32, order="F") if want_V else None
+        self._ck(self.lib.nbmf_samples_VWH_DirBer(self.h, _ptr(Vi, _ip), _ptr(Zs, _ip), F, N, J, K, gamma, alpha, beta,
+                                                  seed, _ptr(Ws, _dp), _ptr(Hs, _dp), _ptr(Vs, _ip)))
+        return {"W_samples": Ws, "H_samples": Hs, "V_samples": Vs}
+
+    def lower_bound_aspect_full(self, E_Z, E_log_W, E_log_H, E_log_1_H, gamma_vb, alpha_vb, beta_vb, alpha, beta,
+                                gamma, V):
+        f = lambda a: np.asfortranarray(a, dtype=np.float64)
+        E_Z, E_log_W, E_log_H, E_log_1_H, gamma_vb, alpha_vb, beta_vb = map(f, (E_Z, E_log_W, E_log_H, E_log_1_H,
+                                                                                   gamma_vb, alpha_vb, beta_vb))
+        Vi = as_imat(V)
+        F, N = Vi.shape
+        K = E_log_W.shape[1]
+        assert E_Z.shape == (F, K, N)
+        lb = C.c_double(0.0)
+        t7 = np.zeros(7)
+        self._ck(self.lib.nbmf_lower_bound_aspect_full(self.h, _ptr(E_Z, _dp), _ptr(E_log_W, _dp), _ptr(E_log_H, _dp),
+                                                       _ptr(E_log_1_H, _dp), _ptr(gamma_vb, _dp), _ptr(alpha_vb, _dp),
+                                                       _ptr(beta_vb, _dp), alpha, beta, gamma, _ptr(Vi, _ip), F, N, K,
+                                                       C.byref(lb), _ptr(t7, _dp)))
+        return lb.value, t7
+
+    # -- measurement aids -----------------------------------------------------
+    def rng_probe(self, which, a, b, seed, n):
+        out = np.zeros(n)
+        self._ck(self.lib.nbmf_debug_rng_probe(self.h, which, a, b, seed, n, _ptr(out, _dp)))
+        return out
+
+    def ffma_peak_tflops(self):
+        t = C.c_double(0.0)
+        self._ck(self.lib.nbmf_debug_ffma_peak(self.h, C.byref(t)))
+        return t.value
+
     # -- predictive LL -----------------------------------------------------
     def predictive_ll(self, E_W, E_H, V_test):
         Vt = as_imat(V_test)
@@ -304,6 +397,116 @@ class Engine:
         self._ck(self.lib.nbmf_predictive_ll(self.h, _ptr(E_W, _dp), _ptr(E_H, _dp), E_W.shape[1],
                                              _ptr(Vt, _ip), F, N, C.byref(ll), C.byref(n)))
         return ll.value, n.value
+
+
+class Group:
+    """One process, several GPUs (nbmf_group_*): the columns of V sharded over `devices`, the F x K
+    statistic exchanged by the library's own NCCL communicator.  Calls take and return whole matrices."""
+
+    def __init__(self, devices, precision: int = _lib.PREC_AUTO, flush_interval: int = 0, pipe_block_cols: int = 0,
+                 planned_iters: int = 0):
+        self.lib = _lib.load()
+        self.g = C.c_void_p()
+        devs = (C.c_int * len(devices))(*devices)
+        opts = NbmfOpts(0, precision, flush_interval, pipe_block_cols, 0, 0, planned_iters, 0)
+        rc = self.lib.nbmf_group_create(C.byref(self.g), C.byref(opts), devs, len(devices))
+        if rc != 0:
+            raise NbmfError(rc, "nbmf_group_create failed")
+        self.size = len(devices)
+        self.F = self.N = 0
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise NbmfError(rc, self.lib.nbmf_group_last_error(self.g).decode())
+
+    def close(self):
+        if getattr(self, "g", None) and self.g:
+            self.lib.nbmf_group_destroy(self.g)
+            self.g = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def columns(self, rank):
+        lo, hi = C.c_int64(0), C.c_int64(0)
+        self._ck(self.lib.nbmf_group_columns(self.g, rank, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
+    def timing(self, rank=0) -> dict:
+        t = NbmfTiming()
+        h = self.lib.nbmf_group_handle(self.g, rank)
+        rc = self.lib.nbmf_get_timing(h, C.byref(t))
+        if rc != 0:
+            raise NbmfError(rc, "nbmf_get_timing")
+        return {k: getattr(t, k) for k, _ in NbmfTiming._fields_}
+
+    def set_data(self, V):
+        V = as_imat(V)
+        self.F, self.N = V.shape
+        self._ck(self.lib.nbmf_group_set_data_i32(self.g, _ptr(V, _ip), self.F, self.N))
+
+    def generate_synthetic(self, F, N, Ktrue, a, b, seed):
+        self.F, self.N = F, N
+        self._ck(self.lib.nbmf_group_generate_synthetic(self.g, F, N, Ktrue, a, b, seed))
+
+    def init_from_labels(self, Z, Kc):
+        Z = as_imat(Z)
+        self._ck(self.lib.nbmf_group_init_from_labels(self.g, _ptr(Z, _ip), Kc))
+
+    def init_random_labels(self, Kc, seed):
+        self._ck(self.lib.nbmf_group_init_random_labels(self.g, Kc, seed))
+
+    def vb_begin(self, K, alpha=1.0, beta=1.0, gamma=1.0, mean_params=False):
+        self._vbK = K
+        self._ck(self.lib.nbmf_group_vb_begin(self.g, K, alpha, beta, gamma, int(mean_params)))
+
+    def vb_step(self, checklb=False):
+        self._ck(self.lib.nbmf_group_vb_step(self.g, int(checklb)))
+
+    def synchronize(self):
+        self._ck(self.lib.nbmf_group_synchronize(self.g))
+
+    def vb_end(self, n_lb=0, want_outputs=True):
+        K = self._vbK
+        E_W = np.zeros((self.F, K), order="F") if want_outputs else None
+        E_H = np.zeros((self.N, K), order="F") if want_outputs else None
+        lbs = np.zeros(max(n_lb, 1))
+        self._ck(self.lib.nbmf_group_vb_end(self.g, _ptr(E_W, _dp), _ptr(E_H, _dp), _ptr(lbs, _dp), n_lb))
+        return E_W, E_H, lbs[:n_lb]
+
+    def vb_aspect(self, V, Z, K, alpha=1.0, beta=1.0, gamma=1.0, iter=100, checklb=False):
+        """VB_Aspect_Rcpp over all devices of the group, one call."""
+        V = as_imat(V); Z = as_imat(Z)
+        self.F, self.N = V.shape
+        E_W = np.zeros((self.F, K), order="F"); E_H = np.zeros((self.N, K), order="F")
+        lbs = np.zeros(max(iter, 1))
+        self._ck(self.lib.nbmf_group_vb_aspect(self.g, _ptr(V, _ip), _ptr(Z, _ip), self.F, self.N, K, alpha, beta, gamma,
+                                               iter, int(checklb), _ptr(E_W, _dp), _ptr(E_H, _dp), _ptr(lbs, _dp)))
+        return E_W, E_H, lbs[:iter]
+
+    def vb_aspect_bits(self, vbits, F, N, K, stats, alpha=1.0, beta=1.0, gamma=1.0, iter=100, checklb=False, out=None):
+        vbits = np.ascontiguousarray(vbits, dtype=np.uint32)
+        assert vbits.shape == (N, (F + 31) // 32)
+        nt, fo, fz = (np.asfortranarray(x, dtype=np.float64) for x in stats)
+        self.F, self.N = F, N
+        if out is not None:
+            E_W, E_H = out
+        else:
+            E_W = np.zeros((F, K), order="F"); E_H = np.zeros((N, K), order="F")
+        lbs = np.zeros(max(iter, 1))
+        self._ck(self.lib.nbmf_group_vb_aspect_bits(self.g, _ptr(vbits, _up), F, N, K, alpha, beta, gamma, iter,
+                                                    int(checklb), _ptr(nt, _dp), _ptr(fo, _dp), _ptr(fz, _dp),
+                                                    _ptr(E_W, _dp), _ptr(E_H, _dp), _ptr(lbs, _dp)))
+        return E_W, E_H, lbs[:iter]
+
+    def gibbs_dirber(self, K, alpha=1.0, beta=1.0, gamma=1.0, iter=100, burnin=0.5, seed=1):
+        E_W = np.zeros((self.F, K), order="F"); E_H = np.zeros((self.N, K), order="F")
+        self._ck(self.lib.nbmf_group_gibbs_dirber(self.g, K, alpha, beta, gamma, iter, burnin, seed, _ptr(E_W, _dp),
+                                                  _ptr(E_H, _dp)))
+        return E_W, E_H
 
 
 # ---------------------------------------------------------------------------

@@ -57,6 +57,22 @@ def make_allreduce_hook(device, group=None):
     return hook
 
 
+def init_library_comm(engine, rank: int, world: int, group=None):
+    """Give the engine its own NCCL communicator (nbmf_comm_init_rank): rank 0 asks the library for a
+    unique id and `torch.distributed` -- any backend -- only ships its 128 bytes.  From then on the
+    library exchanges the F x K statistic itself; no hook is installed."""
+    import torch
+    import torch.distributed as dist
+    if world <= 1:
+        return
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    t = torch.zeros(128, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        t = torch.tensor(list(engine.comm_unique_id()), dtype=torch.uint8, device=dev)
+    dist.broadcast(t, src=0, group=group)
+    engine.comm_init(bytes(t.cpu().tolist()), world, rank)
+
+
 def combine_lowerbounds(terms3: np.ndarray, allreduce_sum) -> np.ndarray:
     """Global ELBO trace from per-rank terms (nbmf_vb_get_lb_terms):
     lb_i = sum_ranks(sum log D + (pH - qH)) + (pW - qW); the row term is replicated.

@@ -280,3 +280,64 @@ def loglikelihood_EV(E_V, V_test):
     Vt = _i32(V_test)
     E_V = np.asfortranarray(E_V, dtype=np.float64)
     return lib().oracle_loglikelihood_EV(_p(E_V), _p(Vt, _ip), Vt.shape[0], Vt.shape[1])
+
+
+def compute_expectation_W(Z_samples, gamma):
+    """compute_expectation_W_Rcpp (collapsed_gibbs_z.cpp:178-197)."""
+    Zs = np.asfortranarray(Z_samples, dtype=np.int32)
+    F, N, J = Zs.shape
+    Kq = int(Zs.max()) + 1
+    E = np.zeros((F, Kq), order="F")
+    assert lib().oracle_compute_expectation_W(_p(Zs, _ip), F, N, J, gamma, Kq, _p(E)) == 0
+    return E
+
+
+def compute_expectation_H(Z_samples, V, alpha, beta):
+    """compute_expectation_H_Rcpp (collapsed_gibbs_z.cpp:230-272), last column left at 0 (:236-242)."""
+    Zs = np.asfortranarray(Z_samples, dtype=np.int32); V = _i32(V)
+    F, N, J = Zs.shape
+    Kq = int(Zs.max()) + 1
+    E = np.zeros((N, Kq), order="F")
+    assert lib().oracle_compute_expectation_H(_p(Zs, _ip), _p(V, _ip), F, N, J, alpha, beta, Kq, _p(E)) == 0
+    return E
+
+
+def lower_bound_aspect(E_Z, E_log_W, E_log_H, E_log_1_H, gamma_vb, alpha_vb, beta_vb, alpha, beta, gamma, V):
+    """lower_bound_aspect (collapsed_gibbs_z_VB.cpp:339-369): (lb, terms7 = pW,pZ,pH,pV,qW,qZ,qH)."""
+    V = _i32(V)
+    F, N = V.shape
+    f = lambda a: np.asfortranarray(a, dtype=np.float64)
+    a = [f(x) for x in (E_Z, E_log_W, E_log_H, E_log_1_H, gamma_vb, alpha_vb, beta_vb)]
+    K = a[1].shape[1]
+    t7 = np.zeros(7)
+    lb = lib().oracle_lower_bound_aspect(*[_p(x) for x in a], alpha, beta, gamma, _p(V, _ip), F, K, N, _p(t7))
+    return lb, t7
+
+
+def sample_gibbs_ZH_column(v_n, W, labels0, alpha=1.0, iter=100, burnin=0.5, seed=1):
+    """One column of the E-step with h collapsed (R/MCEM - sample_gibbs.R:1-37 sample_gibbs_Z, the chain
+    sample_gibbs_cpp, sample_gibbs.cpp:22-80, would run if it stored its draw): NumPy restatement with its
+    own RNG -- compared with the device chain within Monte-Carlo error.  Returns the mean one-hot matrix
+    over the initial state and the kept sweeps (i >= floor(iter*burnin), :73-78)."""
+    rng = np.random.default_rng(seed)
+    v = np.asarray(v_n, dtype=np.int64); W = np.asarray(W, dtype=np.float64)
+    F, K = W.shape
+    lab = np.asarray(labels0, dtype=np.int64).copy()
+    L = np.bincount(lab, minlength=K).astype(np.float64)
+    lik = np.where(v[:, None] == 1, W, 1.0 - W)
+    acc = np.zeros((F, K)); acc[np.arange(F), lab] += 1.0
+    kept = 1
+    nb = int(np.floor(iter * burnin))
+    for i in range(1, iter):
+        u = rng.random(F)
+        for f in range(F):
+            L[lab[f]] -= 1.0
+            p = (alpha + L) * lik[f]
+            c = np.cumsum(p)
+            k = int(np.searchsorted(c, u[f] * c[-1], side="right"))
+            k = min(k, K - 1)
+            lab[f] = k; L[k] += 1.0
+        if i >= nb:
+            acc[np.arange(F), lab] += 1.0
+            kept += 1
+    return acc / kept
