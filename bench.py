@@ -99,51 +99,66 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_run(wl, steps, warmup, sample_F=768, sample_N=1024):
-    """The reference's CPU path (oracle/_ref if built, else the oracle port), 1 thread
-    (the reference is single-threaded), on a bounded sample of the workload."""
+def _time_vb(fn, V, Z, K, gamma, warmup, steps):
+    """seconds for `steps` VB_Aspect_Rcpp iterations: the call includes the one-hot E_Z set-up (as the reference
+    does), so a `warmup`-iteration call and a (`warmup`+`steps`)-iteration call are timed and subtracted"""
+    t0 = time.perf_counter(); fn(V, Z, K, 1.0, 1.0, gamma, iter=max(warmup, 1), checklb=True); t1 = time.perf_counter()
+    fn(V, Z, K, 1.0, 1.0, gamma, iter=max(warmup, 1) + steps, checklb=True); t2 = time.perf_counter()
+    return max((t2 - t1) - (t1 - t0), 1e-9)
+
+
+def cpu_reference_run(wl, steps, warmup, budget_s=25.0, with_port=True):
+    """The reference's CPU path on a bounded sample of the workload: its own sources compiled here
+    (oracle/_ref, kind "reference") when that library travelled to this box, else the oracle port (kind
+    "port").  One thread: VB_Aspect_Rcpp has no threading.  The sample (same generator, same K, fewer rows
+    and columns) is sized from a calibration run so that the whole measurement takes about `budget_s`."""
     from oracle import oracle
+    from oracle import ref as oref
     K = wl["K"]
-    F = min(sample_F, wl["F"]); N = min(sample_N, wl["N"])
+    use_ref = oref.available()
+    fn = oref.vb_aspect if use_ref else oracle.vb_aspect
+    # calibration: 2 iterations on a small sample
+    Fc, Nc = min(128, wl["F"]), min(256, wl["N"])
+    Vc, _, _ = oracle.generate(Fc, Nc, wl["Kt"], wl["a"], wl["b"], wl["seed"])
+    Zc = oracle.random_labels(Vc, K, wl["seed"] + 1)
+    rate = Fc * Nc * K * 2 / _time_vb(fn, Vc, Zc, K, wl["gamma"], 1, 2)          # entries*K / s
+    n_iter = 2 * max(warmup, 1) + steps                                           # iterations the two timed calls run
+    per_iter = budget_s * rate / n_iter                                           # entries*K one iteration may hold
+    N = int(min(wl["N"], 1024))
+    F = int(min(wl["F"], max(32, min(768, per_iter / (K * N)) // 32 * 32)))
+    if F * N * K * 8 > 2e9:                                                       # the reference's E_Z cube (F x K x N doubles)
+        F = max(32, int(2e9 / (8 * N * K)) // 32 * 32)
     V, _, _ = oracle.generate(F, N, wl["Kt"], wl["a"], wl["b"], wl["seed"])
     Z = oracle.random_labels(V, K, wl["seed"] + 1)
-    kind = "port"
-    # checklb=True: the ELBO is evaluated every iteration, as in the GPU arm's timed step
-    fn = lambda it: oracle.vb_aspect(V, Z, K, 1.0, 1.0, wl["gamma"], iter=it, checklb=True)
-    # the oracle call includes the one-hot E_Z init (as the reference does); time a
-    # warmup-iteration call and a (warmup+steps)-iteration call and take the difference
-    t0 = time.perf_counter(); fn(max(warmup, 1)); t1 = time.perf_counter()
-    fn(max(warmup, 1) + steps); t2 = time.perf_counter()
-    dt = max((t2 - t1) - (t1 - t0), 1e-9)
+    dt = _time_vb(fn, V, Z, K, wl["gamma"], warmup, steps)
     val = F * N * K * steps / dt
     extra = {}
-    try:  # the reference's own sources against the shim: bit-identical results, but the shim's eager
-        # containers make it slower than real Armadillo would be, so it is reported, not used as `value`
-        from oracle import ref as oref
-        if oref.available() and F * N * K <= 1 << 25:
-            t3 = time.perf_counter(); oref.vb_aspect(V, Z, K, 1.0, 1.0, wl["gamma"], iter=1, checklb=True); t4 = time.perf_counter()
-            oref.vb_aspect(V, Z, K, 1.0, 1.0, wl["gamma"], iter=3, checklb=True); t5 = time.perf_counter()
-            extra["ref_shim_build_value"] = F * N * K * 2 / max((t5 - t4) - (t4 - t3), 1e-9)
-    except Exception:
-        pass
-    return dict(value=val, unit=UNIT, cores=1, kind=kind,
-                sample=f"{F}x{N} synthetic DirBer (same generator), K={K}, {steps} sequential VB_Aspect_Rcpp "
-                       f"iterations with checklb=TRUE (oracle port, bit-identical to the reference sources compiled against "
-                       f"oracle/ref_shim), 1 thread (the reference has no threading); host has {os.cpu_count()} cores",
-                **extra), dt
+    if use_ref and with_port:   # the loop-for-loop C restatement beside it (no Armadillo stand-in in the way)
+        dtp = _time_vb(oracle.vb_aspect, V, Z, K, wl["gamma"], 1, min(steps, 3))
+        extra["port_value"] = F * N * K * min(steps, 3) / dtp
+    what = ("the reference's own src/collapsed_gibbs_z_VB.cpp compiled against oracle/ref_shim (oracle/_ref)" if use_ref
+            else "oracle port (bit-identical to the reference sources compiled against oracle/ref_shim)")
+    return dict(value=val, unit=UNIT, cores=1, kind="reference" if use_ref else "port",
+                sample=f"{F}x{N} sample of the workload (same DirBer generator and K={K}; the reference cannot hold more: its E_Z cube is "
+                       f"F*K*N doubles), {steps} sequential VB_Aspect_Rcpp iterations with checklb=TRUE after {max(warmup, 1)} warm-up, "
+                       f"{what}, 1 thread (the reference has no threading); host has {os.cpu_count()} cores",
+                sample_F=F, sample_N=N, **extra), dt
 
 
 def run_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 10))
-    cb, dt = cpu_reference_run(wl, steps, min(args.warmup, 2))
+    steps, warmup = max(1, args.steps), max(1, args.warmup)
+    cb, dt = cpu_reference_run(wl, steps, warmup, budget_s=150.0)
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
-            "steps": steps, "warmup": min(args.warmup, 2), "ms_per_step": 1e3 * dt / steps,
+            "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * dt / steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": {"workload": wl["desc"], "F": wl["F"], "N": wl["N"], "K": wl["K"],
-                                            "step": "one VB_aspect iteration: parameters, both statistics, ELBO (checklb=TRUE)"},
+            "data": "synthetic",
+            "config": {"workload": f"{cb['sample_F']}x{cb['sample_N']} sample of: " + wl["desc"] +
+                                   " -- throughput in entries*K/s is what carries over; the reference cannot allocate the full size",
+                       "F": cb["sample_F"], "N": cb["sample_N"], "K": wl["K"], "full_F": wl["F"], "full_N": wl["N"],
+                       "step": "one VB_aspect iteration: parameters, both statistics, ELBO (checklb=TRUE)"},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -288,7 +303,7 @@ def main():
                            if F * N / 8 > 126e6 else "inputs smaller than L2; no flush (latency-sized config)"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof}
         if world == 1 and not args.no_cpu_baseline:
-            cb, _ = cpu_reference_run(wl, 3, 1)
+            cb, _ = cpu_reference_run(wl, 3, 1, budget_s=20.0)
             line["cpu_baseline"] = cb
         print(json.dumps(line), flush=True)
     eng.close()

@@ -1108,7 +1108,7 @@ static int dirber_wavefront(nbmf_handle *h, int K, double alpha, double beta, do
     const int64_t F = h->F, N = h->N;
     if (!h->Z) return fail(h, NBMF_ERR_STATE, "exact wavefront mode needs labels: call nbmf_init_from_labels(Z, K+1)");
     if (h->Kc != Kc) return fail(h, NBMF_ERR_STATE, "statistics must be initialised with Kc = K+1 (collapsed_gibbs_z_VB.cpp:101)");
-    if (h->hook) return fail(h, NBMF_ERR_UNSUPPORTED, "exact wavefront mode is replicas-only (no column sharding)");
+    if (nbmf_sharded(h) && (h->hook || h->comm_world > 1)) return fail(h, NBMF_ERR_UNSUPPORTED, "exact wavefront mode is replicas-only (no column sharding)");
     if ((double)F * N * Kc * 8 > 64e9) return fail(h, NBMF_ERR_UNSUPPORTED, "E_Z does not fit: use NBMF_DIRBER_CONTRACTION");
     double *EZ = nullptr, *buf = nullptr;
     size_t fk = (size_t)F * Kc, nk = (size_t)N * Kc;
@@ -1498,7 +1498,7 @@ static int collapsed_wavefront(nbmf_handle *h, int variant, int K, double alpha,
     if (K <= 0 || iter < 0 || !(alpha > 0) || !(beta > 0) || !(gamma > 0) || !(burnin >= 0) || burnin > 1)
         return fail(h, NBMF_ERR_ARG, "collapsed sampler: bad arguments");
     if (!h->Z) return fail(h, NBMF_ERR_STATE, "the collapsed sweep needs labels: call nbmf_init_from_labels(Z, K)");
-    if (h->hook) return fail(h, NBMF_ERR_UNSUPPORTED, "the collapsed wavefront sweep is replicas-only (no column sharding)");
+    if (nbmf_sharded(h) && (h->hook || h->comm_world > 1)) return fail(h, NBMF_ERR_UNSUPPORTED, "the collapsed wavefront sweep is replicas-only (no column sharding)");
     if (variant == 1 && h->has_na)
         return fail(h, NBMF_ERR_UNSUPPORTED, "Gibbs_DirBer_DP_Rcpp has no NA test (collapsed_gibbs_z.cpp:308-310): V must be fully observed");
     if (variant == 2 && K < 2) return fail(h, NBMF_ERR_ARG, "Gibbs_DirDir_finite_Rcpp needs K >= 2 (a zero entry forbids one component)");

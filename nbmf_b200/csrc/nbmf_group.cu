@@ -12,6 +12,7 @@
 //     nbmf_group_* calls shard the columns of V over the devices, run the per-handle entry points
 //     on the workers and hand back one result, so the Rcpp body stays a single call.
 #include "host_common.h"
+#include "tensor_pass.h"
 #include <nccl.h>
 #include <algorithm>
 #include <condition_variable>
@@ -54,6 +55,7 @@ extern "C" int nbmf_comm_init_rank(nbmf_handle *h, const void *id128, int world,
     ncclComm_t c = nullptr;
     NCCLCK(h, ncclCommInitRank(&c, world, id, rank));
     h->comm = (void *)c; h->comm_rank = rank; h->comm_world = world; h->comm_owned = true;
+    tp_invalidate_data(h);   // exact row counts of the tensor path: to be summed over the new set of ranks
     return NBMF_OK;
 }
 
@@ -69,6 +71,7 @@ extern "C" int nbmf_comm_destroy(nbmf_handle *h)
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     nbmf_comm_release(h);
+    tp_invalidate_data(h);
     return NBMF_OK;
 }
 

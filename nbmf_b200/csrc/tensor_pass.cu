@@ -29,6 +29,7 @@
 // warp 2 TMEM allocator, warp 3 stage-2 issuer, warps 4-19 four epilogue warpgroups (the
 // pipeline and its barriers are described above TPCfg).
 #include "tensor_pass.h"
+#include "host_common.h"
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <algorithm>
@@ -363,9 +364,9 @@ int tp_finalize(nbmf_handle *h)
     if (!s->counts_ready) {
         tp_count_rows_kernel<<<(unsigned)((h->F * 32 + 255) / 256), 256, 0, h->stream>>>(h->mr, h->F, h->Nw, s->cntF);
         tp_count_cols_kernel<<<(unsigned)((h->N * 32 + 255) / 256), 256, 0, h->stream>>>(h->vc, h->mc, h->N, h->Fw, s->cntN);
-        if (h->hook) { // row counts are over ALL columns: sum the ranks' local counts once
-            int rc = h->hook(h->hook_ctx, (void *)s->cntF, (size_t)h->F, (void *)h->stream);
-            if (rc) { h->err = "allreduce hook failed"; return NBMF_ERR_STATE; }
+        if (nbmf_sharded(h)) { // row counts are over ALL columns: sum the ranks' local counts once
+            int rc = nbmf_sum_ranks(h, s->cntF, (size_t)h->F, 0, h->stream);
+            if (rc) return rc;
         }
         s->counts_ready = true;
     }

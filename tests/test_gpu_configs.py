@@ -53,9 +53,12 @@ def test_config2_unvotes100_vb_aspect(gamma):
 
 
 def test_config3_mnist_gibbs_statistical_parity():
-    """Uncollapsed Gibbs (engine) vs the reference's collapsed sampler on MNIST columns, K=16,
-    gamma=1/16: posterior-mean E_V and predictive LL on 10 % held-out pixels agree within the
-    seed-to-seed spread."""
+    """Uncollapsed Gibbs (engine) on MNIST columns, K=16, gamma=1/16, 5 seeds, against (a) the reference's
+    collapsed sampler (Gibbs_DirBer_finite_Rcpp, collapsed_gibbs_z.cpp:363-437, oracle restatement pinned draw
+    for draw to the reference's own code) run long enough to have left its transient (120 sweeps have not:
+    predictive LL -0.223 vs -0.205 at 400) and (b) the oracle's restatement of the engine's own chain with a
+    different RNG: posterior-mean E_V and predictive LL on 10 % held-out pixels agree within the seed-to-seed
+    spread."""
     from nbmf_b200 import Gibbs_DirBer_finite_Rcpp
     V = datasets.mnistbinary_2000()[:, :160]
     F, N = V.shape
@@ -65,21 +68,29 @@ def test_config3_mnist_gibbs_statistical_parity():
     idx = (fi + F * ni).astype(np.int64)
     vt = V[test]
     K = 16
-    ll_ref, ll_gpu, ev_ref, ev_gpu = [], [], [], []
-    for s in (1, 2, 3):
+    ll = lambda p: np.mean(np.log(np.where(vt == 1, p, 1 - p)))
+    ll_ref, ll_unc, ll_gpu, ev_ref, ev_unc, ev_gpu = [], [], [], [], [], []
+    for s in (1, 2, 3, 4, 5):
         Z = oracle.random_labels(tr, K, s)
-        c = oracle.gibbs_dirber_finite(tr, Z, K, 1.0, 1.0, 1.0 / 16, iter=120, burnin=0.5, seed=s)
+        c = oracle.gibbs_dirber_finite(tr, Z, K, 1.0, 1.0, 1.0 / 16, iter=400, burnin=0.5, seed=s)
         _, _, EV = oracle.gibbs_expectation(tr, c["Z_samples"][:, :, :c["written"]], K, 1.0, 1.0, 1.0 / 16)
         p = np.clip(EV[test], 1e-12, 1 - 1e-12)
-        ll_ref.append(np.mean(np.log(np.where(vt == 1, p, 1 - p)))); ev_ref.append(p)
+        ll_ref.append(ll(p)); ev_ref.append(p)
+        u = oracle.gibbs_uncollapsed(tr, Z, K, 1.0, 1.0, 1.0 / 16, iter=800, burnin=0.5, seed=100 + s, want_EV=True)
+        pu = np.clip(u["E_V"][test], 1e-12, 1 - 1e-12)
+        ll_unc.append(ll(pu)); ev_unc.append(pu)
         g = Gibbs_DirBer_finite_Rcpp(tr, Z, K, 1.0, 1.0, 1.0 / 16, 800, 0.5, seed=s, test_idx=idx)
         q = np.clip(g["E_V_test"], 1e-12, 1 - 1e-12)
-        ll_gpu.append(np.mean(np.log(np.where(vt == 1, q, 1 - q)))); ev_gpu.append(q)
-    spread = max(np.ptp(ll_ref), np.ptp(ll_gpu), 0.01)
+        ll_gpu.append(ll(q)); ev_gpu.append(q)
+    print("config3 predictive LL per held-out pixel: collapsed reference", np.round(ll_ref, 4), "uncollapsed oracle",
+          np.round(ll_unc, 4), "engine", np.round(ll_gpu, 4))
+    spread = max(np.ptp(ll_ref), np.ptp(ll_unc), np.ptp(ll_gpu), 0.004)
+    assert abs(np.mean(ll_unc) - np.mean(ll_gpu)) < 1.5 * spread, (ll_unc, ll_gpu)
     assert abs(np.mean(ll_ref) - np.mean(ll_gpu)) < 2 * spread, (ll_ref, ll_gpu)
-    between = np.sqrt(np.mean((np.mean(ev_ref, 0) - np.mean(ev_gpu, 0)) ** 2))
-    within = np.sqrt(np.mean((ev_ref[0] - ev_ref[1]) ** 2))
-    assert between < 2 * max(within, 0.02), (between, within)
+    rms = lambda a, b: np.sqrt(np.mean((a - b) ** 2))
+    within = max(rms(ev_unc[0], ev_unc[1]), rms(ev_gpu[0], ev_gpu[1]), 0.01)
+    assert rms(np.mean(ev_unc, 0), np.mean(ev_gpu, 0)) < 1.5 * within
+    assert rms(np.mean(ev_ref, 0), np.mean(ev_gpu, 0)) < 2 * max(within, rms(ev_ref[0], ev_ref[1]))
     # both beat the marginal-frequency predictor
     base = np.mean(np.log(np.where(vt == 1, V.mean(), 1 - V.mean())))
     assert np.mean(ll_gpu) > base

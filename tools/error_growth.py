@@ -3,8 +3,11 @@
 collapsed_gibbs_z_VB.cpp:376).
 
     python tools/error_growth.py SIZE K CHECKPOINTS [variants] [chunks]
-      variants  comma list of tensor,fast,acc,fp32        (default tensor,fast,acc)
+      variants  comma list of tensor,fast,acc,fp32,pert   (default tensor,fast,acc)
+                pert = the FP64 path again from statistics perturbed by a relative 1e-10: how much the VB
+                map itself amplifies a difference (what any arithmetic other than the reference's shows)
       chunks    comma list of NBMF_TP_CHUNK_STEPS values  (default: library default only)
+      gamma     Dirichlet prior (default 1/K, the reference's experiments' choice)
 
 The FP64 trajectory is computed once; every variant is compared with it at each checkpoint
 (relative Frobenius error of E_W and E_H, max relative ELBO error so far).  Output lines are what
@@ -17,15 +20,20 @@ from nbmf_b200 import Engine, _lib
 F = N = int(sys.argv[1]); K = int(sys.argv[2]); cps = [int(x) for x in sys.argv[3].split(",")]
 variants = (sys.argv[4] if len(sys.argv) > 4 else "tensor,fast,acc").split(",")
 chunks = [int(x) for x in sys.argv[5].split(",")] if len(sys.argv) > 5 else [0]
-gamma = 1.0 / K
+gamma = float(sys.argv[6]) if len(sys.argv) > 6 else 1.0 / K
 PREC = {"fp64": _lib.PREC_FP64, "tensor": _lib.PREC_TENSOR, "fast": _lib.PREC_TENSOR_FAST, "acc": _lib.PREC_TENSOR_ACC,
         "fp32": _lib.PREC_FP32}
 rel = lambda x, y: np.linalg.norm(x - y) / np.linalg.norm(y)
 
 
-def run(prec, ref=None, tag=""):
+def run(prec, ref=None, perturb=0.0):
     e = Engine(precision=prec)
     e.generate_synthetic(F, N, 8, 1.0, 1.0, 3); e.init_random_labels(K, 4)
+    if perturb > 0:
+        rng = np.random.default_rng(1)
+        st = [x * (1.0 + perturb * rng.standard_normal(x.shape)) for x in e.get_stats(K)]
+        e.set_stats(*st)
+        del st
     e.vb_begin(K, 1.0, 1.0, gamma)
     out = {}
     t0 = time.time()
@@ -48,14 +56,19 @@ def run(prec, ref=None, tag=""):
 
 
 ref, lb0, tm0, wall0 = run(PREC["fp64"])
-print(f"F=N={F} K={K} fp64 reference: {wall0 / max(cps) * 1e3:.1f} ms/update wall (path {tm0['path']})", flush=True)
+print(f"F=N={F} K={K} gamma={gamma:.4g} fp64 reference: {wall0 / max(cps) * 1e3:.1f} ms/update wall (path {tm0['path']})", flush=True)
 for ch in chunks:
     if ch > 0:
         os.environ["NBMF_TP_CHUNK_STEPS"] = str(ch)
     else:
         os.environ.pop("NBMF_TP_CHUNK_STEPS", None)
     for name in variants:
-        got, lb, tm, wall = run(PREC[name], ref)
+        if name == "pert":
+            if ch != chunks[0]:
+                continue
+            got, lb, tm, wall = run(PREC["fp64"], ref, perturb=1e-10)
+        else:
+            got, lb, tm, wall = run(PREC[name], ref)
         for i in cps:
             print(f"F=N={F} K={K} chunk={ch or 'default'} {name:6s} after {i:3d} updates: relF E_W {got[i][0]:.2e} E_H {got[i][1]:.2e} "
                   f"ELBO(max over first {i}) {np.max(np.abs(lb[:i] - lb0[:i]) / np.abs(lb0[:i])):.2e}", flush=True)
