@@ -36,7 +36,28 @@ WORKLOADS = {
                 desc="VB_aspect, synthetic DirBer 16384x16384, K=128"),
     "c1": dict(F=200, N=300, K=3, Kt=3, gamma=1.0, a=0.1, b=0.1, seed=1,
                desc="VB_aspect, synthetic DirBer 200x300, K=3 (BASELINE configs[0] shape)"),
+    "c3": dict(F=784, N=60000, K=16, Kt=8, gamma=1.0 / 16, a=0.3, b=1.5, seed=3, kind="gibbs",
+               desc="uncollapsed Gibbs DirBer, synthetic 784x60000 (the shape of data/mnistbinary), K=16 (BASELINE configs[2])"),
 }
+FP64_TENSOR_PEAK_TFLOPS = 40.0
+
+
+def committed_traffic(workload, world, path):
+    """DRAM bytes of the two contraction launches of one iteration from the committed ncu capture of this very
+    command (profiles/*_traffic.json: {"workload", "path", "bytes", "source"}), or None: bench.py does not run
+    under a profiler, so this number is a capture's, labelled as such."""
+    if world != 1:
+        return None, None
+    import glob
+    for fn in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")), reverse=True):
+        try:
+            d = json.load(open(fn))
+        except Exception:
+            continue
+        for rec in (d if isinstance(d, list) else [d]):
+            if rec.get("workload") == workload and int(rec.get("path", -1)) == path:
+                return rec["bytes"], f"committed ncu capture {os.path.relpath(fn, ROOT)}: {rec.get('source', '')}"
+    return None, None
 DTYPES = {0: "f64", 1: "f16 (streamed operand hi+lo in stage 2) / f32 accumulate in TMEM",
           2: "f16 (hi only) / f32 accumulate in TMEM",
           3: "f16 (owner hi+lo in stage 1, streamed hi+lo in stage 2) / f32 accumulate in TMEM", 4: "f32"}
@@ -164,6 +185,87 @@ def run_reference(args, wl):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa(local):
+    """Pin this process (and the pinned host buffers it will first-touch) to the NUMA node of its GPU, so that
+    the ranks of one box do not all stage their PCIe traffic through node 0."""
+    try:
+        bus = subprocess.run(["nvidia-smi", "-i", str(local), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if bus.startswith("00000000:"):
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
+def run_gibbs(args, wl):
+    """--workload c3: the uncollapsed Gibbs sweep (BASELINE configs[2] shape).  A step is one sweep: draw W, H from the
+    counts, sample every entry's label, reduce the counts.  Roofline: the FP32 FMA pipe, whose peak is measured on this
+    device by the library's own saturating kernel."""
+    import torch
+    from nbmf_b200 import Engine
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        raise SystemExit("--workload c3 is a single-GPU line (the sharded Gibbs path is covered by tests)")
+    torch.cuda.set_device(local)
+    F, N, K = wl["F"], wl["N"], wl["K"]
+    eng = Engine(device=local)
+    eng.generate_synthetic(F, N, wl["Kt"], wl["a"], wl["b"], wl["seed"])
+    eng.init_random_labels(K, wl["seed"] + 1)
+    peak = eng.ffma_peak_tflops()
+    eng.gibbs_dirber(K, 1.0, 1.0, wl["gamma"], iter=max(args.warmup, 3) + 1, burnin=0.5, seed=1)
+    sampler = ClockSampler(local); sampler.start(); time.sleep(0.25)
+    eng.gibbs_dirber(K, 1.0, 1.0, wl["gamma"], iter=args.steps + 1, burnin=0.5, seed=2)
+    tim = eng.timing()
+    clocks = sampler.finish()
+    ms = tim["total_ms"]
+    value = F * N * K * args.steps / (ms * 1e-3)
+    # e2e: host int32 V and labels in, posterior means out, one call of the reference-facing entry per step batch
+    e2e = None
+    if not args.no_e2e:
+        from nbmf_b200 import Gibbs_DirBer_finite_Rcpp
+        V = eng.get_data()
+        Z = np.asfortranarray(np.random.default_rng(3).integers(0, K, size=V.shape).astype(np.int32))
+        t0 = time.perf_counter()
+        Gibbs_DirBer_finite_Rcpp(V, Z, K, 1.0, 1.0, wl["gamma"], args.steps + 1, 0.5, seed=2)
+        dt = time.perf_counter() - t0
+        e2e = {"value": F * N * K * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(2 * V.nbytes / args.steps),
+               "d2h_bytes_per_step": int(((F + N) * K * 8 + V.nbytes) / args.steps), "steps": args.steps, "ms_per_step": 1e3 * dt / args.steps,
+               "what": f"one Gibbs_DirBer_finite_Rcpp call of {args.steps} sweeps: host int32 V and Z in, E_W, E_H and the last labels out; bytes are per sweep of that call"}
+    eng.close()
+    flops = 2.0 * F * N * K   # one FMA per entry and component: the running sum of W_fk H_nk^v (1-H_nk)^(1-v)
+    ach = flops * args.steps / (ms * 1e-3) / 1e12
+    line = {"metric": "gibbs_entries_K_per_s", "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32 (probabilities) / int32 (counts)", "data": "synthetic",
+            "config": {"workload": wl["desc"], "F": F, "N": N, "K": K, "step": "one uncollapsed Gibbs sweep (draw W, H; sample Z; reduce counts)",
+                       "l2_policy": "inputs smaller than L2 (5.9 MB bit plane): a sweep is compute/issue bound, no flush"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(tim["launches"]),
+            "roofline": {"bound": "fp32", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if peak else None,
+                         "traffic": None, "peak_source": "FP32 FMA peak measured on this device by nbmf_debug_ffma_peak (saturating FFMA kernel, best of 5)",
+                         "kernel": "gibbs_sweep_kt_kernel + gibbs_draw_kernel, CUDA events around the whole chain inside libnbmf_cuda",
+                         "note": "2 flop per entry*K counted (the running sum); Philox, compares, ballots and histogram updates are integer/issue work on top"}}
+    if not args.no_cpu_baseline:
+        from oracle import oracle
+        Fs, Ns = F, min(N, 200)
+        Vs, _, _ = oracle.generate(Fs, Ns, wl["Kt"], wl["a"], wl["b"], wl["seed"])
+        Zs = oracle.random_labels(Vs, K, 4)
+        t0 = time.perf_counter(); oracle.gibbs_dirber_finite(Vs, Zs, K, 1.0, 1.0, wl["gamma"], iter=3, burnin=0.5, seed=1); t1 = time.perf_counter()
+        oracle.gibbs_dirber_finite(Vs, Zs, K, 1.0, 1.0, wl["gamma"], iter=23, burnin=0.5, seed=1); t2 = time.perf_counter()
+        dtc = max((t2 - t1) - (t1 - t0), 1e-9)
+        line["cpu_baseline"] = {"value": Fs * Ns * K * 20 / dtc, "unit": UNIT, "cores": 1, "kind": "port",
+                                "sample": f"{Fs}x{Ns} columns of the same generator, 20 sweeps of Gibbs_DirBer_finite_Rcpp's collapsed sweep (oracle port, pinned draw for draw to the reference), 1 thread"}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -172,6 +274,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("NBMF_BENCH_WORKLOAD", "c5"), choices=list(WORKLOADS))
     ap.add_argument("--precision", type=int, default=0, help="nbmf_precision (0 auto, 1 fp64, 2 tensor hi+lo, 3 tensor hi only, 4 tensor acc, 5 fp32)")
+    ap.add_argument("--horizon", type=int, default=0, help="AUTO precision: VB updates planned from the start (0 = what this run executes: warmup + steps)")
+    ap.add_argument("--exchange", default="nccl", choices=["nccl", "hook"], help="N>1: the library's own NCCL communicator, or the torch.distributed hook")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -180,14 +284,18 @@ def main():
     if args.impl == "reference":
         run_reference(args, wl)
         return
-
-    import torch
-    import torch.distributed as dist
-    from nbmf_b200 import Engine
-    from nbmf_b200.dist import init_nccl, make_allreduce_hook, shard_columns
+    if wl.get("kind") == "gibbs":
+        run_gibbs(args, wl)
+        return
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    numa = bind_to_gpu_numa(local) if world > 1 else None
+    import torch
+    import torch.distributed as dist
+    from nbmf_b200 import Engine
+    from nbmf_b200.dist import init_library_comm, init_nccl, make_allreduce_hook, shard_columns
+
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
     torch.cuda.set_device(local)
@@ -198,11 +306,16 @@ def main():
     F, N, K = wl["F"], wl["N"], wl["K"]
     n_lo, n_hi = shard_columns(N, rank, world)
     Nl = n_hi - n_lo
+    warm = max(args.warmup, 3)
+    horizon = args.horizon if args.horizon > 0 else warm + args.steps
 
-    eng = Engine(device=local, precision=args.precision, n_global=N if world > 1 else 0, n_offset=n_lo)
+    eng = Engine(device=local, precision=args.precision, n_global=N if world > 1 else 0, n_offset=n_lo, planned_iters=horizon)
     eng.generate_synthetic(F, Nl, wl["Kt"], wl["a"], wl["b"], wl["seed"])
     if world > 1:
-        eng.set_allreduce_hook(make_allreduce_hook(dev))
+        if args.exchange == "nccl":
+            init_library_comm(eng, rank, world)     # torch.distributed only ships the 128-byte id
+        else:
+            eng.set_allreduce_hook(make_allreduce_hook(dev))
     eng.init_random_labels(K, wl["seed"] + 1)
     ext = torch.cuda.ExternalStream(eng.stream, device=dev)
 
@@ -212,7 +325,7 @@ def main():
         torch.cuda.synchronize()
 
     eng.vb_begin(K, 1.0, 1.0, wl["gamma"])
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(warm):
         eng.vb_step(True)
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
@@ -233,11 +346,11 @@ def main():
     eng.vb_end(0, want_outputs=False)
     tim = eng.timing()  # phase split of the last iteration (CUDA events on the engine's stream)
     if world > 1:
-        t = torch.tensor([ms, tim["pass_rows_ms"] + tim["pass_cols_ms"]], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms, tim["pass_rows_ms"] + tim["pass_cols_ms"], tim["exchange_ms"]], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, pass_ms = t[0].item(), t[1].item()
+        ms, pass_ms, xchg_ms = t[0].item(), t[1].item(), t[2].item()
     else:
-        pass_ms = tim["pass_rows_ms"] + tim["pass_cols_ms"]
+        pass_ms = tim["pass_rows_ms"] + tim["pass_cols_ms"]; xchg_ms = tim["exchange_ms"]
     value = F * N * K * args.steps / (ms * 1e-3)
 
     # ---- e2e: host buffers through the C ABI, H2D + D2H inside the timed region ----
@@ -249,17 +362,21 @@ def main():
         vb_host = pv.numpy().view(np.uint32)
         del v, m
         eng.init_random_labels(K, wl["seed"] + 1)
+        root = world == 1 or args.exchange == "hook" or rank == 0   # with the library communicator the row side is rank 0's
 
         def pinned(shape):   # column-major fp64 view of pinned host memory
             t = torch.empty(int(np.prod(shape)), dtype=torch.float64, pin_memory=True)
             return t.numpy().reshape(shape, order="F")
-        st = tuple(pinned(x.shape) for x in eng.get_stats(K))
-        for dst, src in zip(st, eng.get_stats(K)):
-            dst[...] = src
-        outW, outH = pinned((F, K)), pinned((Nl, K))
+        src = eng.get_stats(K)
+        st = tuple((pinned(x.shape) if (i > 0 or root) else None) for i, x in enumerate(src))
+        for dst, x in zip(st, src):
+            if dst is not None:
+                dst[...] = x
+        del src
+        outW, outH = (pinned((F, K)) if root else None), pinned((Nl, K))
         steps_e = max(1, args.e2e_steps)
-        h2d = vb_host.nbytes + sum(x.nbytes for x in st)
-        d2h = (F * K + Nl * K) * 8 + 8
+        h2d = vb_host.nbytes + sum(x.nbytes for x in st if x is not None)
+        d2h = ((F * K if root else 0) + Nl * K) * 8 + 8
         # one untimed call so that buffers exist (a user's second call onward looks like this)
         eng.vb_aspect_bits(vb_host, F, Nl, K, st, 1.0, 1.0, wl["gamma"], iter=1, checklb=True, out=(outW, outH))
         barrier()
@@ -269,36 +386,46 @@ def main():
         barrier()
         dt = time.perf_counter() - t0
         if world > 1:
-            t = torch.tensor([dt], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = t.item()
+            t = torch.tensor([dt, float(h2d), float(d2h)], device=dev, dtype=torch.float64)
+            tm = t.clone(); dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            dt = tm[0].item(); h2d, d2h = t[1].item(), t[2].item()
         e2e = {"value": F * N * K * steps_e / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "steps": steps_e, "ms_per_step": 1e3 * dt / steps_e,
-               "what": "per step: one nbmf_vb_aspect_bits call = host V bit plane + host statistics (pinned) -> 1 iteration with ELBO -> host E_W, E_H; the upload is pipelined with the iteration in column blocks"}
+               "what": "per step: one nbmf_vb_aspect_bits call per rank = host V bit plane + host statistics (pinned) -> 1 iteration with ELBO -> "
+                       "host E_W (rank 0), E_H; the upload is pipelined with the iteration in column blocks; bytes are summed over the ranks"}
 
     if rank == 0:
         peaks = read_peaks()
         flops = 12.0 * F * Nl * K  # 12 flop per entry*K per iteration (this rank's columns)
         ach = flops / (pass_ms * 1e-3) / 1e12 if pass_ms > 0 else 0.0
-        peak = peaks["bf16_sustained"]
-        # DRAM bytes of the two contraction launches of one iteration, from the committed ncu capture of
-        # this very command (profiles/r1_launches_c5.txt): rows 9.82+2.13 GB, cols 9.75+2.13 GB
-        traffic = 23.83e9 if (args.workload == "c5" and world == 1 and int(tim["path"]) == 2) else None
+        path = int(tim["path"])
+        tensor = path in (1, 2, 3)
+        peak = peaks["bf16_sustained"] if tensor else FP64_TENSOR_PEAK_TFLOPS
+        traffic, traffic_src = committed_traffic(args.workload, world, path)
         roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                "traffic": traffic,
-                "traffic_note": "sum over the rows-pass and cols-pass launches of one iteration (ncu dram__bytes_read+write, "
-                                "profiles/r1_launches_c5.txt); algorithmic: V bit plane 2 x 8.6 GB + operands 0.5 GB + chunk partials 4.3 GB write, 4.3 GB read back by the reductions", "peak_source": f"{peaks['source']} bf16 sustained (MEASURED_PEAKS.json)",
+                "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": (f"{peaks['source']} bf16 sustained (MEASURED_PEAKS.json)" if tensor else
+                                "FP64 tensor (DMMA) peak of B200, 40 TFLOP/s nominal: MEASURED_PEAKS.json holds no FP64 figure"),
                 "kernel": "contraction passes (rows + cols) of one iteration, CUDA events inside libnbmf_cuda",
                 "pass_rows_ms": tim["pass_rows_ms"], "pass_cols_ms": tim["pass_cols_ms"],
-                "params_ms": tim["params_ms"], "exchange_ms": tim["exchange_ms"],
-                "frac_of_tf32_nominal_half": ach / (peak / 2.0)}
+                "params_ms": tim["params_ms"], "exchange_ms": xchg_ms,
+                "exchange_note": "device time of the collective on its side stream (it runs beside the cols pass), max over ranks"
+                                 if world > 1 else None}
+        if tensor:
+            roof["frac_of_tf32_nominal_half"] = ach / (peak / 2.0)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "iters_per_s": args.steps / (ms * 1e-3),
+                "warmup": warm, "ms_per_step": ms / args.steps, "iters_per_s": args.steps / (ms * 1e-3),
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                "dtype": DTYPES[int(tim["path"])],
+                "dtype": DTYPES[path],
                 "data": "synthetic",
                 "config": {"workload": wl["desc"], "F": F, "N": N, "K": K, "columns_per_rank": Nl,
                            "step": "one VB_aspect iteration: parameters, both statistics, ELBO (checklb=TRUE)",
+                           "precision": {"requested": args.precision, "path": path, "horizon_updates": horizon,
+                                         "note": "AUTO takes the fastest variant whose measured error growth (profiles/r2_error_growth_*.log) keeps "
+                                                 "W and H inside 1e-5 of the FP64 path for `horizon_updates` updates from the start at this size; "
+                                                 "this run executes warmup + steps updates from its start"},
+                           "exchange": (args.exchange if world > 1 else None), "numa_node": numa,
                            "l2_policy": "inputs larger than L2 (bit planes + operands stream from HBM)"
                            if F * N / 8 > 126e6 else "inputs smaller than L2; no flush (latency-sized config)"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof}

@@ -205,17 +205,25 @@ class Engine:
     def vb_aspect_bits(self, vbits, F, N, K, stats, alpha=1.0, beta=1.0, gamma=1.0, iter=100, checklb=False, out=None):
         """VB_Aspect_Rcpp from host memory in one call (nbmf_vb_aspect_bits): `vbits` the column-packed
         bit plane [N][ceil(F/32)] (no NA), `stats` = (n_total F x K, f_ones N x K, f_zeros N x K)
-        column-major fp64.  The upload overlaps the first iteration when `vbits` is pinned."""
+        column-major fp64.  The upload overlaps the first iteration when `vbits` is pinned.  With a
+        library communicator the row-side arrays belong to rank 0: the other ranks neither upload
+        n_total (it may be None) nor download E_W (returned as None)."""
         vbits = np.ascontiguousarray(vbits, dtype=np.uint32)
         assert vbits.shape == (N, (F + 31) // 32)
-        nt, fo, fz = (np.asfortranarray(x, dtype=np.float64) for x in stats)
-        assert nt.shape == (F, K) and fo.shape == (N, K) and fz.shape == (N, K)
+        rank, world = self.comm_info()
+        root = world <= 1 or rank == 0
+        nt, fo, fz = stats
+        nt = np.asfortranarray(nt, dtype=np.float64) if (root or nt is not None) else None
+        fo = np.asfortranarray(fo, dtype=np.float64); fz = np.asfortranarray(fz, dtype=np.float64)
+        assert (nt is None or nt.shape == (F, K)) and fo.shape == (N, K) and fz.shape == (N, K)
         self.F, self.N = F, N
         if out is not None:
             E_W, E_H = out
-            assert E_W.shape == (F, K) and E_H.shape == (N, K) and E_W.flags.f_contiguous and E_H.flags.f_contiguous
+            assert (E_W is None or (E_W.shape == (F, K) and E_W.flags.f_contiguous)) and E_H.shape == (N, K) and E_H.flags.f_contiguous
         else:
             E_W = np.zeros((F, K), order="F"); E_H = np.zeros((N, K), order="F")
+        if not root:
+            nt = None; E_W = None
         lbs = np.zeros(max(iter, 1))
         self._ck(self.lib.nbmf_vb_aspect_bits(self.h, _ptr(vbits, _up), F, N, K, alpha, beta, gamma, iter, int(checklb),
                                               _ptr(nt, _dp), _ptr(fo, _dp), _ptr(fz, _dp), _ptr(E_W, _dp), _ptr(E_H, _dp),
@@ -657,53 +665,41 @@ def Gibbs_DirBer(V, Z, K, alpha=1.0, beta=1.0, gamma=1.0, iter=100, burnin=0.5, 
     return res
 
 
-# -- host-side mirrors of the posterior-mean helpers the R wrappers apply to the sample cubes ----------
+# -- the posterior-mean helpers the R wrappers apply to the sample cubes, on the device ----------------
 # (compute_expectation_W_Rcpp :178-197, compute_expectation_H_Rcpp :230-272,
-#  compute_expectation_H_dirdir_Rcpp :205-225; O(F N J) integer reductions on cubes that are already on
-#  the host -- post-processing, not the hot path)
-def compute_expectation_W_Rcpp(Z_samples, gamma):
+#  compute_expectation_H_dirdir_Rcpp :205-225; O(F N J K) in the reference)
+def _with_engine(device, fn):
+    e = Engine(device=device, precision=_lib.PREC_FP64)
+    try:
+        return fn(e)
+    finally:
+        e.close()
+
+
+def compute_expectation_W_Rcpp(Z_samples, gamma, *, device=0):
     """normalise(gamma + mean_j n_total_j) over max(label)+1 columns; NA labels count for nothing."""
-    Zs = np.asarray(Z_samples)
-    F, N, J = Zs.shape
-    K = int(Zs.max()) + 1
-    E = np.empty((F, K), order="F")
-    for k in range(K):
-        E[:, k] = gamma + (Zs == k).sum(axis=(1, 2)) / J
-    return np.asfortranarray(E / E.sum(axis=1, keepdims=True))
+    return _with_engine(device, lambda e: e.compute_expectation_W(Z_samples, gamma))
 
 
-def compute_expectation_H_Rcpp(Z_samples, V, alpha, beta):
+def compute_expectation_H_Rcpp(Z_samples, V, alpha, beta, *, device=0):
     """mean_j (alpha + ones_j) / (alpha + beta + total_j); the reference's k loop stops at max(label), so
     the last column stays zero (:236-242) -- kept."""
-    Zs = np.asarray(Z_samples); Vi = as_imat(V)
-    F, N, J = Zs.shape
-    K = int(Zs.max()) + 1
-    obs = (Vi != NA_INTEGER)[:, :, None]
-    one = (Vi == 1)[:, :, None]
-    E = np.zeros((N, K), order="F")
-    for k in range(K - 1):
-        m = (Zs == k) & obs
-        ones = (m & one).sum(axis=0); tot = m.sum(axis=0)          # N x J
-        E[:, k] = ((alpha + ones) / (alpha + beta + tot)).mean(axis=1)
-    return E
+    return _with_engine(device, lambda e: e.compute_expectation_H(Z_samples, V, alpha, beta))
 
 
-def compute_expectation_H_dirdir_Rcpp(C_samples, alpha):
-    """normalise(alpha + mean_j column counts of C) (generic_Gibbs_DirDir.R:40-43)."""
-    Cs = np.asarray(C_samples)
-    F, N, J = Cs.shape
-    K = int(Cs.max()) + 1
-    E = np.empty((N, K), order="F")
-    for k in range(K):
-        E[:, k] = alpha + (Cs == k).sum(axis=(0, 2)) / J
-    return np.asfortranarray(E / E.sum(axis=1, keepdims=True))
+def compute_expectation_H_dirdir_Rcpp(C_samples, alpha, *, device=0):
+    """normalise(alpha + mean_j column counts of C) (:205-225, generic_Gibbs_DirDir.R:40-43): the W reducer
+    applied to the cube with rows and columns exchanged."""
+    Ct = np.asfortranarray(np.transpose(np.asarray(C_samples), (1, 0, 2)))
+    return _with_engine(device, lambda e: e.compute_expectation_W(Ct, alpha))
 
 
 def Gibbs_DirBer_DP(V, Z, alpha=1.0, beta=1.0, gamma=1.0, iter=100, burnin=0.5, **kw):
     """R/generic_Gibbs_DirBer_DP.R:1-28."""
     res = Gibbs_DirBer_DP_Rcpp(V, _zero_base(Z), alpha, beta, gamma, iter, burnin, **kw)
-    res["E_W"] = compute_expectation_W_Rcpp(res["Z_samples"], gamma)
-    res["E_H"] = compute_expectation_H_Rcpp(res["Z_samples"], V, alpha, beta)
+    dev = kw.get("device", 0)
+    res["E_W"] = compute_expectation_W_Rcpp(res["Z_samples"], gamma, device=dev)
+    res["E_H"] = compute_expectation_H_Rcpp(res["Z_samples"], V, alpha, beta, device=dev)
     _check_nonneg(res)
     res.update(alpha=alpha, beta=beta, gamma=gamma)
     res["class"] = ("GibbsDirBer", "Bernoulli")
@@ -713,8 +709,9 @@ def Gibbs_DirBer_DP(V, Z, alpha=1.0, beta=1.0, gamma=1.0, iter=100, burnin=0.5, 
 def Gibbs_DirDir(V, Z, K, alpha=1.0, gamma=1.0, iter=100, burnin=0.5, **kw):
     """R/generic_Gibbs_DirDir.R:1-34."""
     res = Gibbs_DirDir_finite_Rcpp(V, _zero_base(Z), K, alpha, gamma, iter, burnin, **kw)
-    res["E_W"] = compute_expectation_W_Rcpp(res["Z_samples"], gamma)
-    res["E_H"] = compute_expectation_H_dirdir_Rcpp(res["C_samples"], alpha)
+    dev = kw.get("device", 0)
+    res["E_W"] = compute_expectation_W_Rcpp(res["Z_samples"], gamma, device=dev)
+    res["E_H"] = compute_expectation_H_dirdir_Rcpp(res["C_samples"], alpha, device=dev)
     _check_nonneg(res)
     Vi = as_imat(V)
     if res["E_W"].shape[0] != Vi.shape[0] or res["E_H"].shape[0] != Vi.shape[1]:

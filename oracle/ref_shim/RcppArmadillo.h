@@ -123,6 +123,7 @@ public:
     const T *begin() const { return d.data(); }
     T *end() { return d.data() + n_elem; }
     T *memptr() { return d.data(); }
+    const T *memptr() const { return d.data(); }
     Vec &zeros() { std::fill(d.begin(), d.end(), T(0)); return *this; }
     Vec &fill(T v) { std::fill(d.begin(), d.end(), v); return *this; }
     void set_size(uword n) { d.assign(n, T(0)); n_elem = n; }
@@ -187,6 +188,7 @@ public:
     Cube &zeros() { std::fill(d.begin(), d.end(), T(0)); return *this; }
     T max() const { return *std::max_element(d.begin(), d.end()); }
     T *memptr() { return d.data(); }
+    const T *memptr() const { return d.data(); }
     Cube &operator+=(const Cube &o) { for (uword i = 0; i < n_elem; i++) d[i] += o.d[i]; return *this; }
     template <class Fn> Cube &transform(Fn f) { for (uword i = 0; i < n_elem; i++) d[i] = f(d[i]); return *this; }
 };

@@ -1,11 +1,14 @@
-"""Host-side mirrors in nbmf_b200/api.py that need no GPU: the posterior-mean helpers the R wrappers apply to
-the sample cubes (compute_expectation_*_Rcpp), checked against the oracle's restatements."""
+"""The posterior-mean helpers the R wrappers apply to the sample cubes (compute_expectation_*_Rcpp), as the
+package exposes them under the reference's names -- device reducers since round 2 -- checked against the
+oracle's restatements."""
 import numpy as np
+import pytest
 
 from nbmf_b200.api import (compute_expectation_H_dirdir_Rcpp, compute_expectation_H_Rcpp, compute_expectation_W_Rcpp)
 from oracle import oracle
 
 NA = oracle.NA
+pytestmark = pytest.mark.gpu
 
 
 def _samples(F=14, N=19, K=4, J=7, na=0.2, seed=3):
