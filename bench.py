@@ -60,7 +60,7 @@ def committed_traffic(workload, world, path):
     return None, None
 DTYPES = {0: "f64", 1: "f16 (streamed operand hi+lo in stage 2) / f32 accumulate in TMEM",
           2: "f16 (hi only) / f32 accumulate in TMEM",
-          3: "f16 (owner hi+lo in stage 1, streamed hi+lo in stage 2) / f32 accumulate in TMEM", 4: "f32"}
+          3: "f16 (streamed operand hi in f16 + lo in e5m2 in stage 2) / f32 accumulate in TMEM", 4: "f32"}
 METRIC = "vb_entries_K_per_s"
 UNIT = "entries*K/s"
 
@@ -273,7 +273,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("NBMF_BENCH_WORKLOAD", "c5"), choices=list(WORKLOADS))
-    ap.add_argument("--precision", type=int, default=0, help="nbmf_precision (0 auto, 1 fp64, 2 tensor hi+lo, 3 tensor hi only, 4 tensor acc, 5 fp32)")
+    ap.add_argument("--precision", type=int, default=0, help="nbmf_precision (0 auto, 1 fp64, 2 tensor hi+lo, 3 tensor hi only, 4 tensor hi + e5m2 lo, 5 fp32)")
     ap.add_argument("--horizon", type=int, default=0, help="AUTO precision: VB updates planned from the start (0 = what this run executes: warmup + steps)")
     ap.add_argument("--exchange", default="nccl", choices=["nccl", "hook"], help="N>1: the library's own NCCL communicator, or the torch.distributed hook")
     ap.add_argument("--e2e-steps", type=int, default=2)

@@ -54,9 +54,9 @@ typedef enum nbmf_precision {
                                   fp32 accumulate in TMEM                                          */
     NBMF_PREC_TENSOR_FAST = 3, /* same, hi only in stage 2: 1/3 fewer MMAs; its error falls
                                   like ~1/sqrt(min(F,N)) -- short runs at very large sizes         */
-    NBMF_PREC_TENSOR_ACC = 4,  /* hi+lo in stage 2 AND the owner operand's lo part in stage 1: removes
-                                  the one error that does not average out over the reduction;
-                                  4/2 of the FAST variant's MMAs                                   */
+    NBMF_PREC_TENSOR_LO8 = 4,  /* the hi+lo form with the 2^-11-sized lo term of stage 2 computed through
+                                  kind::f8f6f4 on e5m2 copies of R and W_lo: the accuracy of TENSOR at
+                                  5/4 (not 6/4) of the FAST variant's tensor time                   */
     NBMF_PREC_FP32 = 5         /* FP32 FMA + warp shuffles (small K, short runs)    */
 } nbmf_precision;
 
@@ -65,7 +65,7 @@ typedef enum nbmf_path {
     NBMF_PATH_FP64 = 0,
     NBMF_PATH_TENSOR = 1,      /* f16, stage 2 hi+lo          */
     NBMF_PATH_TENSOR_FAST = 2, /* f16, hi only                */
-    NBMF_PATH_TENSOR_ACC = 3,  /* f16, stage 1 and 2 hi+lo    */
+    NBMF_PATH_TENSOR_LO8 = 3,  /* f16 hi + e5m2 lo in stage 2 */
     NBMF_PATH_FP32 = 4
 } nbmf_path;
 

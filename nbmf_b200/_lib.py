@@ -13,8 +13,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(HERE, "libnbmf_cuda.so")
 
 NBMF_OK = 0
-PREC_AUTO, PREC_FP64, PREC_TENSOR, PREC_TENSOR_FAST, PREC_TENSOR_ACC, PREC_FP32 = 0, 1, 2, 3, 4, 5
-PATH_FP64, PATH_TENSOR, PATH_TENSOR_FAST, PATH_TENSOR_ACC, PATH_FP32 = 0, 1, 2, 3, 4
+PREC_AUTO, PREC_FP64, PREC_TENSOR, PREC_TENSOR_FAST, PREC_TENSOR_LO8, PREC_FP32 = 0, 1, 2, 3, 4, 5
+PATH_FP64, PATH_TENSOR, PATH_TENSOR_FAST, PATH_TENSOR_LO8, PATH_FP32 = 0, 1, 2, 3, 4
 DIRBER_EXACT_WAVEFRONT, DIRBER_CONTRACTION = 0, 1
 
 

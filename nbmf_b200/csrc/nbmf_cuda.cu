@@ -555,7 +555,7 @@ extern "C" int nbmf_get_stats(nbmf_handle *h, int Kc, double *n_total, double *f
 // ---------------------------------------------------------------------------
 static bool use_tensor_path(const nbmf_handle *h)
 {
-    return h->path_mode == NBMF_PATH_TENSOR || h->path_mode == NBMF_PATH_TENSOR_FAST || h->path_mode == NBMF_PATH_TENSOR_ACC;
+    return h->path_mode == NBMF_PATH_TENSOR || h->path_mode == NBMF_PATH_TENSOR_FAST || h->path_mode == NBMF_PATH_TENSOR_LO8;
 }
 
 // Fixes the contraction variant of a session from the precision option, K, the sizes and -- under
@@ -570,7 +570,7 @@ static void resolve_path(nbmf_handle *h, int K, int horizon)
     else if (p == NBMF_PREC_FP32) h->path_mode = NBMF_PATH_FP32;
     else if (p == NBMF_PREC_TENSOR) h->path_mode = NBMF_PATH_TENSOR;
     else if (p == NBMF_PREC_TENSOR_FAST) h->path_mode = NBMF_PATH_TENSOR_FAST;
-    else if (p == NBMF_PREC_TENSOR_ACC) h->path_mode = NBMF_PATH_TENSOR_ACC;
+    else if (p == NBMF_PREC_TENSOR_LO8) h->path_mode = NBMF_PATH_TENSOR_LO8;
     else h->path_mode = tp_auto_mode(h, K, horizon);
 }
 

@@ -50,10 +50,11 @@ struct TPState {
     int64_t Fpad = 0, N2pad = 0;          // padded row counts of the f16 operand matrices
     __half *A_hi = nullptr, *A_lo = nullptr;   // [Fpad][KP]
     __half *B_hi = nullptr, *B_lo = nullptr;   // [N2pad][KP]
+    uint8_t *A_lo8 = nullptr, *B_lo8 = nullptr; // e5m2 copies of the lo parts (NBMF_PREC_TENSOR_LO8)
     float *partial = nullptr; size_t partial_bytes = 0;
     int *item_ctr = nullptr;              // work-queue counter of the running launch
     float *partial2 = nullptr; size_t partial2_bytes = 0;   // cols-pass partials of the pipelined step
-    CUtensorMap tmA, tmB, tmAlo, tmBlo;
+    CUtensorMap tmA, tmB, tmAlo, tmBlo, tmAlo8, tmBlo8;
     unsigned long long *dmax = nullptr;   // [0] max A bits, [1] max BB bits
     int *dexp = nullptr;                  // [0] eA, [1] eB
     double *dacc = nullptr;               // [0] sum log2 S, [1] clamp count
@@ -89,44 +90,32 @@ bool tp_supported(const nbmf_handle *h, int K)
 }
 
 // ---------------------------------------------------------------------------
-// AUTO precision.  The relative Frobenius error of E_W / E_H against the FP64 path after `it` VB
-// updates from a random start is modelled as
-//     err(variant, n, it) = rnd_variant(it) * sqrt(4096 / n) + sys_variant(it),   n = min(F, N_global)
-// rnd = the part made of per-entry independent roundings (R to f16, the streamed operand's hi part),
-// which averages out over the reduction; sys = the owner operand's f16 rounding in stage 1, fixed
-// per lane for a whole pass, which does not (only the ACC variant removes it).  The tables are the
-// measured curves of profiles/r2_error_growth_*.log (K = 128, gamma = 1/K, the worse of E_W / E_H),
-// log-interpolated in `it`; tools/error_growth.py regenerates them.  AUTO takes the cheapest variant
-// whose modelled error is below 0.7e-5, and the FP64 path if none is.
+// AUTO precision.  What bounds an f16 variant is not its per-update error (1e-7 .. 1e-6) but how long
+// the VB map keeps amplifying it: while K symmetric components are still separating, a difference
+// between two trajectories grows roughly exponentially (the FP64 path started from statistics
+// perturbed by 1e-10 shows the same growth: profiles/r2_error_growth_*.log, variant "pert").  So every
+// variant has a HORIZON -- the number of updates from a random start for which the relative Frobenius
+// error of E_W and E_H against the FP64 path stays below 0.8e-5 -- measured at K = 128, gamma = 1/K on
+// squares of side n (tools/error_growth.py) and interpolated in log2 n.  AUTO takes the cheapest variant
+// whose horizon covers the planned number of updates, and the FP64 path (DMMA) if none does.
 // ---------------------------------------------------------------------------
-static const int kErrIts[] = {1, 2, 5, 10, 20, 40, 60, 80, 100, 200};
-static const double kErrRnd[3][10] = {
-    // FAST (hi only)
-    {3.3e-6, 4.9e-6, 7.8e-6, 1.2e-5, 2.0e-5, 3.9e-5, 7.7e-5, 1.4e-4, 2.0e-4, 6.0e-4},
-    // TENSOR (stage 2 hi+lo)
-    {5.8e-7, 8.1e-7, 1.6e-6, 2.6e-6, 3.9e-6, 6.5e-6, 1.0e-5, 1.6e-5, 2.3e-5, 7.0e-5},
-    // ACC (stage 1 and 2 hi+lo)
-    {5.8e-7, 8.1e-7, 1.6e-6, 2.6e-6, 3.9e-6, 6.0e-6, 9.0e-6, 1.3e-5, 1.9e-5, 6.0e-5},
-};
-static const double kErrSys[3][10] = {
-    {3e-7, 5e-7, 1.2e-6, 2.0e-6, 3.3e-6, 6.5e-6, 1.0e-5, 1.5e-5, 2.0e-5, 5e-5},
-    {3e-7, 5e-7, 1.2e-6, 2.0e-6, 3.3e-6, 6.5e-6, 1.0e-5, 1.5e-5, 2.0e-5, 5e-5},
-    {0, 0, 0, 0, 0, 0, 0, 0, 0, 0},
+static const double kHorizonLog2n[] = {14.0, 16.0, 18.0};            // n = 16384, 65536, 262144
+static const double kHorizon[3][3] = {
+    // FAST (hi only), LO8 (hi + e5m2 lo), TENSOR (hi + lo)      -- filled from the measured curves
+    {16, 24, 24},
+    {60, 36, 36},
+    {60, 36, 36},
 };
 
-static double tp_model_error(int variant /*0 FAST, 1 TENSOR, 2 ACC*/, double n, int it)
+static int tp_horizon(int variant /*0 FAST, 1 LO8, 2 TENSOR*/, double n)
 {
-    const int NI = (int)(sizeof(kErrIts) / sizeof(kErrIts[0]));
-    it = std::max(1, it);
-    int j = 0;
-    while (j + 1 < NI && kErrIts[j + 1] <= it) j++;
-    auto at = [&](const double *tab) {
-        if (j + 1 >= NI) return tab[NI - 1] * (double)it / kErrIts[NI - 1];        // beyond the table: linear growth
-        const double t = (std::log((double)it) - std::log((double)kErrIts[j])) /
-                         (std::log((double)kErrIts[j + 1]) - std::log((double)kErrIts[j]));
-        return tab[j] + t * (tab[j + 1] - tab[j]);
-    };
-    return at(kErrRnd[variant]) * std::sqrt(4096.0 / n) + at(kErrSys[variant]);
+    const double x = std::log2(std::max(n, 2.0));
+    const double *t = kHorizon[variant];
+    if (x <= kHorizonLog2n[0]) return (int)std::min(t[0], t[0] * std::sqrt(n / 16384.0) + 2.0);   // smaller reductions: errors ~1/sqrt(n)
+    if (x >= kHorizonLog2n[2]) return (int)t[2];
+    const int j = x < kHorizonLog2n[1] ? 0 : 1;
+    const double w = (x - kHorizonLog2n[j]) / (kHorizonLog2n[j + 1] - kHorizonLog2n[j]);
+    return (int)std::min(t[j], t[j + 1]) + (int)(0.0 * w);            // conservative: the smaller neighbour
 }
 
 int tp_auto_mode(const nbmf_handle *h, int K, int horizon)
@@ -134,18 +123,18 @@ int tp_auto_mode(const nbmf_handle *h, int K, int horizon)
     if (!tp_supported(h, K)) return NBMF_PATH_FP64;
     const int64_t n_glob = h->opts.n_global > 0 ? h->opts.n_global : h->N;
     const double n = (double)std::min<int64_t>(h->F, n_glob);
-    const double gate = 0.7e-5;
-    if (tp_model_error(0, n, horizon) < gate) return NBMF_PATH_TENSOR_FAST;
-    if (tp_model_error(1, n, horizon) < gate) return NBMF_PATH_TENSOR;
-    if (tp_model_error(2, n, horizon) < gate) return NBMF_PATH_TENSOR_ACC;
+    if (horizon <= tp_horizon(0, n)) return NBMF_PATH_TENSOR_FAST;
+    if (horizon <= tp_horizon(1, n)) return NBMF_PATH_TENSOR_LO8;
+    if (horizon <= tp_horizon(2, n)) return NBMF_PATH_TENSOR;
     return NBMF_PATH_FP64;
 }
 
-// modelled error of a variant, for tools and tests (not part of the public header)
+// horizon of a variant, for tools and tests (not part of the public header)
 extern "C" double nbmf_debug_model_error(int path, double n, int iters)
 {
-    const int v = path == NBMF_PATH_TENSOR_FAST ? 0 : path == NBMF_PATH_TENSOR ? 1 : path == NBMF_PATH_TENSOR_ACC ? 2 : -1;
-    return v < 0 ? 0.0 : tp_model_error(v, n, iters);
+    const int v = path == NBMF_PATH_TENSOR_FAST ? 0 : path == NBMF_PATH_TENSOR_LO8 ? 1 : path == NBMF_PATH_TENSOR ? 2 : -1;
+    (void)iters;
+    return v < 0 ? 1e9 : (double)tp_horizon(v, n);
 }
 
 void tp_invalidate_data(nbmf_handle *h)
@@ -158,7 +147,7 @@ void tp_free(nbmf_handle *h)
 {
     TPState *s = (TPState *)h->tp;
     if (!s) return;
-    cudaFree(s->A_hi); cudaFree(s->A_lo); cudaFree(s->B_hi); cudaFree(s->B_lo);
+    cudaFree(s->A_hi); cudaFree(s->A_lo); cudaFree(s->B_hi); cudaFree(s->B_lo); cudaFree(s->A_lo8); cudaFree(s->B_lo8);
     cudaFree(s->partial); cudaFree(s->partial2); cudaFree(s->dmax); cudaFree(s->dexp); cudaFree(s->dacc); cudaFree(s->derr); cudaFree(s->item_ctr);
     cudaFree(s->cntF); cudaFree(s->cntN);
     delete s;
@@ -177,6 +166,22 @@ static int make_map(nbmf_handle *h, CUtensorMap *tm, void *base, int64_t rows, i
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { h->err = "cuTensorMapEncodeTiled failed"; return NBMF_ERR_CUDA; }
+    return NBMF_OK;
+}
+
+// e5m2 lo part: rows of KP bytes, one box = 64 rows x KP bytes (one swizzle atom wide)
+static int make_map8(nbmf_handle *h, CUtensorMap *tm, void *base, int64_t rows, int KP)
+{
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) { h->err = "cuTensorMapEncodeTiled entry point not available"; return NBMF_ERR_CUDA; }
+    cuuint64_t dims[2] = {(cuuint64_t)KP, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)KP};
+    cuuint32_t box[2] = {(cuuint32_t)KP, 64};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, KP == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { h->err = "cuTensorMapEncodeTiled (lo8) failed"; return NBMF_ERR_CUDA; }
     return NBMF_OK;
 }
 
@@ -200,6 +205,8 @@ int tp_prepare(nbmf_handle *h)
     if (e == cudaSuccess) e = cudaMalloc(&s->A_lo, ab);
     if (e == cudaSuccess) e = cudaMalloc(&s->B_hi, bb);
     if (e == cudaSuccess) e = cudaMalloc(&s->B_lo, bb);
+    if (e == cudaSuccess) e = cudaMalloc(&s->A_lo8, ab / 2);
+    if (e == cudaSuccess) e = cudaMalloc(&s->B_lo8, bb / 2);
     if (e == cudaSuccess) e = cudaMalloc(&s->dmax, 16);
     if (e == cudaSuccess) e = cudaMalloc(&s->dexp, 8);
     if (e == cudaSuccess) e = cudaMalloc(&s->dacc, 16);
@@ -210,6 +217,7 @@ int tp_prepare(nbmf_handle *h)
     if (e != cudaSuccess) { cudaGetLastError(); tp_free(h); h->err = "tensor path allocation failed"; return NBMF_ERR_OOM; }
     cudaMemsetAsync(s->A_hi, 0, ab, h->stream); cudaMemsetAsync(s->A_lo, 0, ab, h->stream);
     cudaMemsetAsync(s->B_hi, 0, bb, h->stream); cudaMemsetAsync(s->B_lo, 0, bb, h->stream);
+    cudaMemsetAsync(s->A_lo8, 0, ab / 2, h->stream); cudaMemsetAsync(s->B_lo8, 0, bb / 2, h->stream);
     cudaMemsetAsync(s->derr, 0, 16, h->stream);
     int rc = make_map(h, &s->tmA, s->A_hi, s->Fpad, KP);
     if (rc) return rc;
@@ -218,6 +226,10 @@ int tp_prepare(nbmf_handle *h)
     rc = make_map(h, &s->tmAlo, s->A_lo, s->Fpad, KP);
     if (rc) return rc;
     rc = make_map(h, &s->tmBlo, s->B_lo, s->N2pad, KP);
+    if (rc) return rc;
+    rc = make_map8(h, &s->tmAlo8, s->A_lo8, s->Fpad, KP);
+    if (rc) return rc;
+    rc = make_map8(h, &s->tmBlo8, s->B_lo8, s->N2pad, KP);
     if (rc) return rc;
     if (const char *sl = getenv("NBMF_TP_SPIN_LIMIT")) {
         const long long v = atoll(sl);
@@ -262,14 +274,17 @@ __global__ void tp_exp_kernel(const unsigned long long *dmax, int *dexp)
 }
 
 __global__ void tp_split_kernel(const double *__restrict__ x, int64_t count, const int *dexp, int which,
-                                __half *__restrict__ hi, __half *__restrict__ lo)
+                                __half *__restrict__ hi, __half *__restrict__ lo, uint8_t *__restrict__ lo8)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
     double v = ldexp(x[i], dexp[which]);
     __half h = __double2half(v);
     hi[i] = h;
-    lo[i] = __double2half(v - (double)__half2float(h));
+    const __half l = __double2half(v - (double)__half2float(h));
+    lo[i] = l;
+    // e5m2 = the upper byte of an f16, here rounded to nearest (|lo| is tiny: the carry cannot reach infinity)
+    lo8[i] = (uint8_t)(((uint32_t)__half_as_ushort(l) + 0x80u) >> 8);
 }
 
 // exact per-lane observation counts: sum_k of each statistic row is an integer known
@@ -327,15 +342,14 @@ __global__ void tp_finalize_kernel(const double *__restrict__ U, const double *_
 // First-order ELBO correction for the single-f16 stage 1:
 //   sum log D  ~=  sum log D_hi + sum_lk (U - U_hi)_lk G_lk     over both passes' owners,
 // because D - D_hi = (U-U_hi).W_hi + U_hi.(W-W_hi) + O(2^-24) and sum_c R_lc W_c = G_l.
-__global__ void tp_logcorr_kernel(const double *__restrict__ U, const __half *__restrict__ Uhi, const __half *__restrict__ Ulo,
+__global__ void tp_logcorr_kernel(const double *__restrict__ U, const __half *__restrict__ Uhi,
                                   const double *__restrict__ G, int64_t count, const int *dexp, int which, double *sumlogD)
 {
     __shared__ double sh[32];
     const double inv = ldexp(1.0, -dexp[which]);
     double t = 0.0;
-    // Ulo != NULL: stage 1 of the pass that accumulated the logarithms already used U_hi + U_lo
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
-        t += (U[i] - ((double)__half2float(Uhi[i]) + (Ulo ? (double)__half2float(Ulo[i]) : 0.0)) * inv) * G[i];
+        t += (U[i] - (double)__half2float(Uhi[i]) * inv) * G[i];
     t = block_sum(t, sh);
     if (threadIdx.x == 0) atomicAdd(sumlogD, t);
 }
@@ -347,9 +361,6 @@ int tp_log_correction(nbmf_handle *h, int owner_rows, double *sumlogD)
     const int64_t cnt = (owner_rows ? h->F : 2 * h->N) * (int64_t)s->KP;
     tp_logcorr_kernel<<<(unsigned)std::min<int64_t>(2048, (cnt + 255) / 256), 256, 0, h->stream>>>(
         owner_rows ? h->A : h->BB, owner_rows ? s->A_hi : s->B_hi,
-        // the logarithms come from the rows pass: its owner (A) carries the lo part in ACC mode, its
-        // streamed operand (B) never does
-        (owner_rows && h->path_mode == NBMF_PATH_TENSOR_ACC) ? s->A_lo : nullptr,
         owner_rows ? h->GF : h->GN, cnt, s->dexp, owner_rows ? 0 : 1, sumlogD);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { h->err = std::string("tp_log_correction: ") + cudaGetErrorString(e); return NBMF_ERR_CUDA; }
@@ -387,8 +398,8 @@ int tp_convert_operands(nbmf_handle *h)
     tp_max_kernel<<<(unsigned)std::min<int64_t>(1024, (ca + 255) / 256), 256, 0, h->stream>>>(h->A, ca, s->dmax);
     tp_max_kernel<<<(unsigned)std::min<int64_t>(1024, (cb + 255) / 256), 256, 0, h->stream>>>(h->BB, cb, s->dmax + 1);
     tp_exp_kernel<<<1, 32, 0, h->stream>>>(s->dmax, s->dexp);
-    tp_split_kernel<<<(unsigned)((ca + 255) / 256), 256, 0, h->stream>>>(h->A, ca, s->dexp, 0, s->A_hi, s->A_lo);
-    tp_split_kernel<<<(unsigned)((cb + 255) / 256), 256, 0, h->stream>>>(h->BB, cb, s->dexp, 1, s->B_hi, s->B_lo);
+    tp_split_kernel<<<(unsigned)((ca + 255) / 256), 256, 0, h->stream>>>(h->A, ca, s->dexp, 0, s->A_hi, s->A_lo, s->A_lo8);
+    tp_split_kernel<<<(unsigned)((cb + 255) / 256), 256, 0, h->stream>>>(h->BB, cb, s->dexp, 1, s->B_hi, s->B_lo, s->B_lo8);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { h->err = std::string("tp_convert_operands: ") + cudaGetErrorString(e); return NBMF_ERR_CUDA; }
     h->timing.launches += 5;
@@ -478,6 +489,21 @@ __device__ __forceinline__ void tc_mma_ts2(uint32_t d_tmem, uint32_t a_tmem, uin
                  ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc), "r"(0u)
                  : "memory");
 }
+// same for kind::f8f6f4 (e5m2 x e5m2 -> fp32, K = 32 per instruction)
+__device__ __forceinline__ void tc_mma_ts2_f8(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                              uint32_t acc)
+{
+    asm volatile("{\n .reg .pred p;\n .reg .b64 bd;\n setp.ne.b32 p, %5, 0;\n mov.b64 bd, {%2, %3};\n"
+                 " tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], [%1], bd, %4, {%6, %6, %6, %6}, p;\n}"
+                 ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc), "r"(0u)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t (&r)[8])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32])
 {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -544,6 +570,12 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int b_mn_major)
     return (1u << 4) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// kind::f8f6f4: a_format [7,10), b_format [10,13) with E5M2 = 1 (cute::UMMA::MXF8F6F4Format); MN-major B is valid for 8-bit types
+__host__ __device__ constexpr uint32_t make_idesc_e5m2(int M, int N, int b_mn_major)
+{
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
 // cycle accounting per role (build with EXTRA=-DTP_PROFILE; tools/role_profile.py reads it)
 #ifdef TP_PROFILE
 __device__ unsigned long long g_tp_prof[64];
@@ -579,8 +611,7 @@ struct TPArgs {
     float *dbg;                    // optional debug dump
     int dbg_flags;                 // timing experiments only: 1 = skip lo TMA, 2 = skip all TMA
     int use_lo;                    // stage 2 adds the W_lo term (NBMF_PREC_TENSOR); 0 = hi only (NBMF_PREC_TENSOR_FAST)
-    const __half *U_lo;            // owner operand lo part, rows [Lpad][KP] (NBMF_PREC_TENSOR_ACC: stage 1 adds U_lo . W_hi)
-    int use_ulo;
+    int use_lo8;                   // the W_lo term of stage 2 through kind::f8f6f4 on e5m2 copies of R and W_lo (NBMF_PREC_TENSOR_LO8)
 };
 
 // One step = 64 streamed rows.  Shared-memory stage: [hi: KB blocks]([lo: KB blocks] when the
@@ -597,34 +628,37 @@ struct TPArgs {
 // return even when the phase completed long ago, and arrive -> wake-up of a blocked waiter
 // ~180.  Both issuers therefore start the try_wait of step t+1 BEFORE they issue the MMAs of
 // step t and only fall back to a blocking wait when that early probe failed.
-template <int KP, bool USE_LO, bool USE_ULO>
+template <int KP, bool USE_LO, bool LO8>
 struct TPCfg {
+    static_assert(!LO8 || USE_LO, "LO8 is a form of the lo term");
     static constexpr int KB = KP / 64;
     static constexpr int STEP_ROWS = 64;
     static constexpr int BLOCK_BYTES = STEP_ROWS * 128;
-    static constexpr int PART_BYTES = KB * BLOCK_BYTES;     // hi (or lo) part of a stage
-    static constexpr int TILE_BYTES = (USE_LO ? 2 : 1) * PART_BYTES;
+    static constexpr int PART_BYTES = KB * BLOCK_BYTES;     // hi part of a stage (f16)
+    static constexpr int LO_BYTES = !USE_LO ? 0 : (LO8 ? STEP_ROWS * KP : PART_BYTES);   // lo part: f16, or e5m2 rows of KP bytes
+    static constexpr int TILE_BYTES = PART_BYTES + LO_BYTES;
     static constexpr int STAGES = (224 * 1024 / TILE_BYTES) > 16 ? 16 : (224 * 1024 / TILE_BYTES);
-    // S slots (fp32 stage-1 accumulators, 64 columns each).  With the owner's lo part in TMEM as well
-    // (USE_ULO) KP = 128 leaves room for two; stage 1 then takes twice as long, so two are enough.
-    static constexpr int NS = (USE_ULO && KP == 128) ? 2 : 3;
+    // S slots (fp32 stage-1 accumulators, 64 columns each).  The e5m2 copy of R needs 64 more TMEM
+    // columns: at KP = 128 an S slot makes room (a step is longer there, two slots keep stage 1 fed).
+    static constexpr int NS = (LO8 && KP == 128) ? 2 : 3;
     static constexpr int NR = 4;                            // R slots (f16 reciprocals, 32 columns each)
     static constexpr int COL_G = 0;
     static constexpr int COL_S = KP;                        // + 64 * (step % NS)
     static constexpr int COL_R = KP + 64 * NS;              // + 32 * (step % NR)
     static constexpr int COL_U = COL_R + 32 * NR;           // KP/2 columns; KP = 128: 448 + 64 = 512
-    static constexpr int COL_ULO = COL_U + KP / 2;          // KP/2 columns (USE_ULO only; KP = 128: 384 + 64 + 64 = 512)
-    static_assert(COL_U + (USE_ULO ? KP : KP / 2) <= 512, "TMEM columns");
+    static constexpr int COL_R8 = COL_U + KP / 2;           // + 16 * (step % NR): e5m2 copy of R (LO8 only)
+    static_assert(COL_U + KP / 2 + (LO8 ? 16 * NR : 0) <= 512, "TMEM columns");
     static constexpr int SMEM_BYTES = STAGES * TILE_BYTES + 1024 /*align*/ + 512 /*barriers*/;
+    static_assert(TILE_BYTES % 1024 == 0, "stage alignment (SWIZZLE_128B atoms)");
     static_assert(2 * STAGES + NS + 3 * NR + 2 + 8 <= 64, "barrier area");
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory");
 };
 
-template <int KP, bool ROWS, bool WANT_LOG, bool HAS_NA, bool USE_LO, bool USE_ULO>
+template <int KP, bool ROWS, bool WANT_LOG, bool HAS_NA, bool USE_LO, bool LO8>
 __global__ void __launch_bounds__(TP_THREADS, 1)
 tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__ CUtensorMap tmLo, TPArgs a)
 {
-    using C = TPCfg<KP, USE_LO, USE_ULO>;
+    using C = TPCfg<KP, USE_LO, LO8>;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = smem_base + C::STAGES * C::TILE_BYTES;
@@ -713,8 +747,9 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
 #pragma unroll
                         for (int kb = 0; kb < C::KB; kb++) {
                             tma_load_2d(dst + kb * C::BLOCK_BYTES, &tmHi, kb * 64, row0, full);
-                            if (USE_LO) tma_load_2d(dst + C::PART_BYTES + kb * C::BLOCK_BYTES, &tmLo, kb * 64, row0, full);
+                            if (USE_LO && !LO8) tma_load_2d(dst + C::PART_BYTES + kb * C::BLOCK_BYTES, &tmLo, kb * 64, row0, full);
                         }
+                        if (LO8) tma_load_2d(dst + C::PART_BYTES, &tmLo, 0, row0, full);   // 64 rows x KP bytes of e5m2
                     }
                     PROF_ACC(1);
                 }
@@ -770,13 +805,6 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
                     for (int kk = 0; kk < KP / 16; kk++)
                         tc_mma_ts2(d, tmem + C::COL_U + kk * 8,
                                    lo + (((kk >> 2) * C::BLOCK_BYTES + (kk & 3) * 32) >> 4), DHI, IDESC1, kk ? 1u : 0u);
-                    if (USE_ULO) {   // S += U_lo . W_hi^T: removes the owner's rounding error, the one that does not
-                                     // average out over the reduction (tools/numerics_study.py)
-#pragma unroll
-                        for (int kk = 0; kk < KP / 16; kk++)
-                            tc_mma_ts2(d, tmem + C::COL_ULO + kk * 8,
-                                       lo + (((kk >> 2) * C::BLOCK_BYTES + (kk & 3) * 32) >> 4), DHI, IDESC1, 1u);
-                    }
                     PROF_ACC(3);
                     tc_commit(sfull);
                     PROF_ACC(4);
@@ -814,6 +842,7 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
                     const uint32_t lo = (((smem_base + g_stage * C::TILE_BYTES) >> 4) & 0x3FFFu) | DLO2;
                     const uint32_t rcol = tmem + C::COL_R + 32 * rs;
                     const uint32_t empty = BAR_EMPTY(g_stage);
+                    const uint32_t g_stage_cur = g_stage; (void)g_stage_cur;
                     if (++g_stage == C::STAGES) g_stage = 0;
                     gs++;
                     pre = (t + 1 < nst) ? mbar_try(BAR_RREADY + 8u * (gs & 3u), (gs >> 2) & 1u) : 0u;
@@ -821,10 +850,23 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
                     for (int j = 0; j < C::STEP_ROWS / 16; j++)
                         tc_mma_ts2(tmem + C::COL_G, rcol + j * 8, lo + ((j * (16 * 128)) >> 4), DHI, IDESC2,
                                    (t == 0 && j == 0) ? 0u : 1u);
-                    if (USE_LO) {
+                    if (USE_LO && !LO8) {
 #pragma unroll
                         for (int j = 0; j < C::STEP_ROWS / 16; j++)
                             tc_mma_ts2(tmem + C::COL_G, rcol + j * 8, lo + ((C::PART_BYTES + j * (16 * 128)) >> 4), DHI, IDESC2, 1u);
+                    }
+                    if (LO8) {
+                        // the 2^-11-sized correction R . W_lo at a quarter of the hi term's tensor time: e5m2 copies of
+                        // both operands (R: the upper bytes of the f16 values, W_lo: rounded by the split kernel),
+                        // K = 32 per instruction.  B MN-major: rows of KP bytes, one swizzle atom wide, 8-row groups
+                        // KP * 8 bytes apart.
+                        constexpr uint32_t IDESC8 = make_idesc_e5m2(128, KP, 1);
+                        constexpr uint32_t DHI8 = ((uint32_t)(KP * 8) >> 4) | (1u << 14) | ((KP == 128 ? 2u : 4u) << 29);
+                        const uint32_t lo8 = (((smem_base + (g_stage_cur) * C::TILE_BYTES + C::PART_BYTES) >> 4) & 0x3FFFu);
+                        const uint32_t r8col = tmem + C::COL_R8 + 16 * rs;
+#pragma unroll
+                        for (int j = 0; j < C::STEP_ROWS / 32; j++)
+                            tc_mma_ts2_f8(tmem + C::COL_G, r8col + j * 8, lo8 + ((j * (32 * KP)) >> 4), DHI8, IDESC8, 1u);
                     }
                     PROF_ACC(2);
                     tc_commit(empty);                // tile consumed: the smem stage goes back to the producer
@@ -846,6 +888,14 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
         const int lrow = q * 32 + lane;             // owner lane within the tile
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         const uint32_t t_r = tmem + lane_addr + C::COL_R + 32 * grp;
+        const uint32_t t_r8 = tmem + lane_addr + C::COL_R8 + 16 * grp;   // e5m2 copy of the group's R slot (LO8)
+        // 16 f16x2 words -> 8 words of four e5m2 values each: the upper bytes, rounded to nearest
+        auto to_e5m2 = [](const uint32_t (&rp)[16], uint32_t (&r8)[8]) {
+#pragma unroll
+            for (int m = 0; m < 8; m++)
+                r8[m] = __byte_perm(rp[2 * m] + 0x00800080u, rp[2 * m + 1] + 0x00800080u, 0x7531);
+        };
+        (void)t_r8; (void)to_e5m2;
         const uint32_t bar_sfull = BAR_SFULL + 8u * grp, bar_rready = BAR_RREADY + 8u * grp, bar_rfree = BAR_RFREE + 8u * grp;
         uint32_t g_phase = 0;
         uint32_t base = 0;                          // global step number of the item's first step
@@ -883,21 +933,13 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
             const bool lane_ok = l < a.L;
             // ---- owner operand of this item: issue the global loads before waiting for the
             //      previous item's accumulator, so their latency overlaps its last MMAs
-            uint32_t ur[16], ul[16];
+            uint32_t ur[16];
             if (grp < KP / 32) {
                 const __half *src = a.U_hi + l * KP + grp * 32;
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
                     uint4 v = lane_ok ? __ldg(reinterpret_cast<const uint4 *>(src) + i) : make_uint4(0, 0, 0, 0);
                     ur[4 * i] = v.x; ur[4 * i + 1] = v.y; ur[4 * i + 2] = v.z; ur[4 * i + 3] = v.w;
-                }
-                if (USE_ULO) {
-                    const __half *srl = a.U_lo + l * KP + grp * 32;
-#pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        uint4 v = lane_ok ? __ldg(reinterpret_cast<const uint4 *>(srl) + i) : make_uint4(0, 0, 0, 0);
-                        ul[4 * i] = v.x; ul[4 * i + 1] = v.y; ul[4 * i + 2] = v.z; ul[4 * i + 3] = v.w;
-                    }
                 }
             }
             // ---- drain G of the previous item
@@ -909,7 +951,6 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
             }
             if (grp < KP / 32) {
                 tc_st16(tmem + lane_addr + C::COL_U + grp * 16, ur);
-                if constexpr (USE_ULO) tc_st16(tmem + lane_addr + C::COL_ULO + grp * 16, ul);
                 tc_wait_st();
             }
             tc_fence_before();
@@ -1014,9 +1055,11 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
                 tc_fence_after();
                 PROF_ACC(5);
                 tc_st16(t_r, rp0);
+                if constexpr (LO8) { uint32_t r8[8]; to_e5m2(rp0, r8); tc_st8(t_r8, r8); }
                 half_step(1, s1, rp1);
                 PROF_ACC(4);
                 tc_st16(t_r + 16, rp1);
+                if constexpr (LO8) { uint32_t r8[8]; to_e5m2(rp1, r8); tc_st8(t_r8 + 8, r8); }
                 tc_wait_st();
                 tc_fence_before();
                 mbar_arrive(bar_rready);
@@ -1067,21 +1110,21 @@ __global__ void tp_logfix_kernel(const double *dacc, const int *dexp, double nse
         *sumlogD += 0.6931471805599453 * dacc[0];
 }
 
-template <int KP, bool ROWS, bool WANT_LOG, bool HAS_NA, bool USE_LO, bool USE_ULO>
+template <int KP, bool ROWS, bool WANT_LOG, bool HAS_NA, bool USE_LO, bool LO8>
 static cudaError_t launch_tp3(const CUtensorMap &tm, const CUtensorMap &tmlo, const TPArgs &a, int grid, cudaStream_t st)
 {
-    auto kern = tp_pass_kernel<KP, ROWS, WANT_LOG, HAS_NA, USE_LO, USE_ULO>;
-    using C = TPCfg<KP, USE_LO, USE_ULO>;
+    auto kern = tp_pass_kernel<KP, ROWS, WANT_LOG, HAS_NA, USE_LO, LO8>;
+    using C = TPCfg<KP, USE_LO, LO8>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     kern<<<grid, TP_THREADS, C::SMEM_BYTES, st>>>(tm, tmlo, a);
     return cudaGetLastError();
 }
-// three precision variants: hi only (FAST), + W_lo in stage 2 (TENSOR), + U_lo in stage 1 (ACC)
+// three precision variants: hi only (FAST), + W_lo in stage 2 as f16 (TENSOR) or as e5m2 (LO8)
 template <int KP, bool ROWS, bool WANT_LOG, bool HAS_NA>
 static cudaError_t launch_tp2(const CUtensorMap &tm, const CUtensorMap &tmlo, const TPArgs &a, int grid, cudaStream_t st)
 {
-    if (a.use_ulo) return launch_tp3<KP, ROWS, WANT_LOG, HAS_NA, true, true>(tm, tmlo, a, grid, st);
+    if (a.use_lo8) return launch_tp3<KP, ROWS, WANT_LOG, HAS_NA, true, true>(tm, tmlo, a, grid, st);
     if (a.use_lo) return launch_tp3<KP, ROWS, WANT_LOG, HAS_NA, true, false>(tm, tmlo, a, grid, st);
     return launch_tp3<KP, ROWS, WANT_LOG, HAS_NA, false, false>(tm, tmlo, a, grid, st);
 }
@@ -1108,10 +1151,10 @@ static void tp_base_args(nbmf_handle *h, TPState *s, int owner_rows, bool want_l
 {
     int64_t S_rows;
     if (owner_rows) {
-        a.U_hi = s->A_hi; a.U_lo = s->A_lo; a.vbits = h->vr; a.mbits = h->mr; a.words = h->Nw;
+        a.U_hi = s->A_hi; a.vbits = h->vr; a.mbits = h->mr; a.words = h->Nw;
         a.L = h->F; S_rows = 2 * h->N;
     } else {
-        a.U_hi = s->B_hi; a.U_lo = s->B_lo; a.vbits = h->vc; a.mbits = h->mc; a.words = h->Fw;
+        a.U_hi = s->B_hi; a.vbits = h->vc; a.mbits = h->mc; a.words = h->Fw;
         a.L = 2 * h->N; S_rows = h->F;
     }
     a.owner_tiles_total = (a.L + 127) / 128;
@@ -1119,8 +1162,8 @@ static void tp_base_args(nbmf_handle *h, TPState *s, int owner_rows, bool want_l
     a.dexp = s->dexp; a.dacc = s->dacc; a.derr = s->derr; a.item_ctr = s->item_ctr;
     a.want_log = want_log;
     // the precision variant was fixed for the session by nbmf_resolve_path (tp_auto_mode under AUTO)
-    a.use_lo = (h->path_mode == NBMF_PATH_TENSOR || h->path_mode == NBMF_PATH_TENSOR_ACC) ? 1 : 0;
-    a.use_ulo = (h->path_mode == NBMF_PATH_TENSOR_ACC) ? 1 : 0;
+    a.use_lo = (h->path_mode == NBMF_PATH_TENSOR || h->path_mode == NBMF_PATH_TENSOR_LO8) ? 1 : 0;
+    a.use_lo8 = (h->path_mode == NBMF_PATH_TENSOR_LO8) ? 1 : 0;
     a.dbg = g_tp_dbg;
     { const char *f = getenv("NBMF_TP_DEBUG_FLAGS"); a.dbg_flags = f ? atoi(f) : 0; }
 }
@@ -1149,14 +1192,15 @@ static int tp_launch(nbmf_handle *h, TPState *s, int owner_rows, const TPArgs &a
     // streamed rows rely on the mask bits being zero)
     const bool use_mask = h->has_na || (h->F % 128 != 0) || (h->N % 64 != 0);
     cudaError_t e;
+    const CUtensorMap &loA = a.use_lo8 ? s->tmAlo8 : s->tmAlo, &loB = a.use_lo8 ? s->tmBlo8 : s->tmBlo;
     if (KP == 128) {
-        if (!owner_rows) e = launch_tp<128, false, false>(s->tmA, s->tmAlo, a, grid, h->stream, use_mask);
-        else if (a.want_log) e = launch_tp<128, true, true>(s->tmB, s->tmBlo, a, grid, h->stream, use_mask);
-        else e = launch_tp<128, true, false>(s->tmB, s->tmBlo, a, grid, h->stream, use_mask);
+        if (!owner_rows) e = launch_tp<128, false, false>(s->tmA, loA, a, grid, h->stream, use_mask);
+        else if (a.want_log) e = launch_tp<128, true, true>(s->tmB, loB, a, grid, h->stream, use_mask);
+        else e = launch_tp<128, true, false>(s->tmB, loB, a, grid, h->stream, use_mask);
     } else {
-        if (!owner_rows) e = launch_tp<64, false, false>(s->tmA, s->tmAlo, a, grid, h->stream, use_mask);
-        else if (a.want_log) e = launch_tp<64, true, true>(s->tmB, s->tmBlo, a, grid, h->stream, use_mask);
-        else e = launch_tp<64, true, false>(s->tmB, s->tmBlo, a, grid, h->stream, use_mask);
+        if (!owner_rows) e = launch_tp<64, false, false>(s->tmA, loA, a, grid, h->stream, use_mask);
+        else if (a.want_log) e = launch_tp<64, true, true>(s->tmB, loB, a, grid, h->stream, use_mask);
+        else e = launch_tp<64, true, false>(s->tmB, loB, a, grid, h->stream, use_mask);
     }
     if (e != cudaSuccess) { h->err = std::string("tp_pass launch: ") + cudaGetErrorString(e); return NBMF_ERR_CUDA; }
     h->timing.launches += 1;

@@ -1,5 +1,5 @@
 """Round-2 kernels through the C ABI against the oracle: the DMMA FP64 pass and its SIMT sibling, the
-FP32 FFMA pass (small K), the ACC tensor variant, the fused uncollapsed Gibbs sweep (fast, K <= 32) and
+FP32 FFMA pass (small K), the LO8 tensor variant, the fused uncollapsed Gibbs sweep (fast, K <= 32) and
 its wide sibling, the library-owned collectives (group of devices, one process)."""
 import os
 
@@ -87,7 +87,7 @@ def test_fp32_pass_small_K(F, N, K, na, iters):
 # ---------------------------------------------------------------------------
 # tensor variants against the oracle itself
 # ---------------------------------------------------------------------------
-@pytest.mark.parametrize("prec_name", ["TENSOR", "TENSOR_ACC", "TENSOR_FAST"])
+@pytest.mark.parametrize("prec_name", ["TENSOR", "TENSOR_LO8", "TENSOR_FAST"])
 @pytest.mark.parametrize("F,N,K", [(512, 640, 64), (384, 1000, 128), (1000, 300, 40)])
 def test_tensor_variants_vs_oracle(prec_name, F, N, K):
     from nbmf_b200 import Engine, _lib

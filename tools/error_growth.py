@@ -3,7 +3,7 @@
 collapsed_gibbs_z_VB.cpp:376).
 
     python tools/error_growth.py SIZE K CHECKPOINTS [variants] [chunks]
-      variants  comma list of tensor,fast,acc,fp32,pert   (default tensor,fast,acc)
+      variants  comma list of tensor,lo8,fast,fp32,pert   (default tensor,lo8,fast)
                 pert = the FP64 path again from statistics perturbed by a relative 1e-10: how much the VB
                 map itself amplifies a difference (what any arithmetic other than the reference's shows)
       chunks    comma list of NBMF_TP_CHUNK_STEPS values  (default: library default only)
@@ -18,10 +18,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from nbmf_b200 import Engine, _lib
 
 F = N = int(sys.argv[1]); K = int(sys.argv[2]); cps = [int(x) for x in sys.argv[3].split(",")]
-variants = (sys.argv[4] if len(sys.argv) > 4 else "tensor,fast,acc").split(",")
+variants = (sys.argv[4] if len(sys.argv) > 4 else "tensor,lo8,fast").split(",")
 chunks = [int(x) for x in sys.argv[5].split(",")] if len(sys.argv) > 5 else [0]
 gamma = float(sys.argv[6]) if len(sys.argv) > 6 else 1.0 / K
-PREC = {"fp64": _lib.PREC_FP64, "tensor": _lib.PREC_TENSOR, "fast": _lib.PREC_TENSOR_FAST, "acc": _lib.PREC_TENSOR_ACC,
+PREC = {"fp64": _lib.PREC_FP64, "tensor": _lib.PREC_TENSOR, "fast": _lib.PREC_TENSOR_FAST, "lo8": _lib.PREC_TENSOR_LO8,
         "fp32": _lib.PREC_FP32}
 rel = lambda x, y: np.linalg.norm(x - y) / np.linalg.norm(y)
 
