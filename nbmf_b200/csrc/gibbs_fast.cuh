@@ -158,20 +158,21 @@ __global__ void __launch_bounds__(256) gibbs_draw_kernel(GibbsDrawArgs a)
             a.h_cur[n * K + lane] = (float)hm;
         }
         if (a.draw && lane < KT) {
-            float hv = 0.5f;
+            float hv = 0.5f, cv = 0.5f;
             if (lane < K) {
                 const int64_t ng = n + a.n_offset;
                 PhiloxF rs(a.seed, (uint32_t)ng, (uint32_t)lane | 0x80000000u | ((uint32_t)(ng >> 32) << 16), a.sweep);
                 float lx, ly;
                 const float x = rs.gamma_log((float)(a.alpha + c1), &lx);
                 const float y = rs.gamma_log((float)(a.beta + c0), &ly);
-                // x e^lx / (x e^lx + y e^ly) through the difference of the logarithms (no underflow for shapes << 1)
+                // H = x e^lx / (x e^lx + y e^ly) and 1 - H, each through the difference of the logarithms: no
+                // underflow for shapes << 1 and no cancellation in the complement when H is within 1e-8 of 1
                 const float dl = (logf(y) + ly) - (logf(x) + lx);
-                hv = 1.0f / (1.0f + expf(dl));
-                hv = fminf(fmaxf(hv, 1e-30f), 1.0f - 5.96e-8f);
+                hv = fmaxf(1.0f / (1.0f + expf(dl)), 1e-30f);
+                cv = fmaxf(1.0f / (1.0f + expf(-dl)), 1e-30f);
             }
             a.HH[(a.N + n) * KT + lane] = hv;
-            a.HH[n * KT + lane] = lane < K ? 1.0f - hv : 0.5f;
+            a.HH[n * KT + lane] = cv;
         }
     }
 }

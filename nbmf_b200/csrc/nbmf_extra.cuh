@@ -320,7 +320,8 @@ extern "C" int nbmf_samples_VWH_DirBer(nbmf_handle *h, const int32_t *V, const i
 
 // Gamma / Beta / Dirichlet draws of the device samplers, exposed for the distribution tests
 // (tests/test_gpu_rng.py): which = 0 Gamma(a) fp64 stream, 1 Gamma(a) fp32 stream (gibbs_fast.cuh),
-// 2 Beta(a, b) fp32 stream as the Gibbs draw kernel forms it.
+// 2 Beta(a, b) fp32 stream as the Gibbs draw kernel forms it, 3 the same draw as its logit log(H / (1 - H)) (Beta with
+// shapes << 1 puts most of its mass closer to 0 and 1 than a double resolves).
 __global__ void rng_probe_kernel(int which, double a, double b, uint64_t seed, int64_t n, double *out)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -338,7 +339,7 @@ __global__ void rng_probe_kernel(int which, double a, double b, uint64_t seed, i
         float lx, ly;
         const float x = rs.gamma_log((float)a, &lx), y = rs.gamma_log((float)b, &ly);
         const float dl = (logf(y) + ly) - (logf(x) + lx);
-        out[i] = 1.0 / (1.0 + exp((double)dl));
+        out[i] = which == 3 ? -(double)dl : 1.0 / (1.0 + exp((double)dl));
     }
 }
 extern "C" int nbmf_debug_rng_probe(nbmf_handle *h, int which, double a, double b, uint64_t seed, int64_t n, double *out)

@@ -100,22 +100,26 @@ bool tp_supported(const nbmf_handle *h, int K)
 // whose horizon covers the planned number of updates, and the FP64 path (DMMA) if none does.
 // ---------------------------------------------------------------------------
 static const double kHorizonLog2n[] = {14.0, 16.0, 18.0};            // n = 16384, 65536, 262144
-static const double kHorizon[3][3] = {
-    // FAST (hi only), LO8 (hi + e5m2 lo), TENSOR (hi + lo)      -- filled from the measured curves
-    {16, 24, 24},
-    {60, 36, 36},
-    {60, 36, 36},
+static const double kHorizon[2][3] = {
+    // profiles/r2_error_growth_{16k,64k,c5}.log: last checkpoint (interpolated) with max(E_W, E_H) error <= 0.8e-5
+    {16, 23, 31},        // FAST (hi only), chunks of 512 steps
+    {64, 39, 57},        // LO8 (hi + e5m2 lo), chunks of 128 steps: the fp32 accumulation chain in TMEM is the other error source
 };
 
-static int tp_horizon(int variant /*0 FAST, 1 LO8, 2 TENSOR*/, double n)
+static int tp_horizon(int variant /*0 FAST, 1 LO8*/, double n)
 {
     const double x = std::log2(std::max(n, 2.0));
     const double *t = kHorizon[variant];
-    if (x <= kHorizonLog2n[0]) return (int)std::min(t[0], t[0] * std::sqrt(n / 16384.0) + 2.0);   // smaller reductions: errors ~1/sqrt(n)
-    if (x >= kHorizonLog2n[2]) return (int)t[2];
-    const int j = x < kHorizonLog2n[1] ? 0 : 1;
-    const double w = (x - kHorizonLog2n[j]) / (kHorizonLog2n[j + 1] - kHorizonLog2n[j]);
-    return (int)std::min(t[j], t[j + 1]) + (int)(0.0 * w);            // conservative: the smaller neighbour
+    double hz;
+    if (x <= kHorizonLog2n[0])       // shorter reductions: the per-entry rounding errors average out less (~1/sqrt(n) per update)
+        hz = variant == 0 ? t[0] * (n / 16384.0) : t[0] * std::sqrt(n / 16384.0);
+    else if (x >= kHorizonLog2n[2]) hz = t[2];
+    else {
+        const int j = x < kHorizonLog2n[1] ? 0 : 1;
+        const double w = (x - kHorizonLog2n[j]) / (kHorizonLog2n[j + 1] - kHorizonLog2n[j]);
+        hz = 0.9 * std::exp((1.0 - w) * std::log(t[j]) + w * std::log(t[j + 1]));   // between anchors: log-linear, 10 % margin
+    }
+    return (int)std::floor(hz);
 }
 
 int tp_auto_mode(const nbmf_handle *h, int K, int horizon)
@@ -125,14 +129,13 @@ int tp_auto_mode(const nbmf_handle *h, int K, int horizon)
     const double n = (double)std::min<int64_t>(h->F, n_glob);
     if (horizon <= tp_horizon(0, n)) return NBMF_PATH_TENSOR_FAST;
     if (horizon <= tp_horizon(1, n)) return NBMF_PATH_TENSOR_LO8;
-    if (horizon <= tp_horizon(2, n)) return NBMF_PATH_TENSOR;
     return NBMF_PATH_FP64;
 }
 
 // horizon of a variant, for tools and tests (not part of the public header)
 extern "C" double nbmf_debug_model_error(int path, double n, int iters)
 {
-    const int v = path == NBMF_PATH_TENSOR_FAST ? 0 : path == NBMF_PATH_TENSOR_LO8 ? 1 : path == NBMF_PATH_TENSOR ? 2 : -1;
+    const int v = path == NBMF_PATH_TENSOR_FAST ? 0 : (path == NBMF_PATH_TENSOR_LO8 || path == NBMF_PATH_TENSOR) ? 1 : -1;
     (void)iters;
     return v < 0 ? 1e9 : (double)tp_horizon(v, n);
 }
@@ -169,6 +172,18 @@ static int make_map(nbmf_handle *h, CUtensorMap *tm, void *base, int64_t rows, i
     return NBMF_OK;
 }
 
+// Steps per chunk = length of an fp32 accumulation chain in TMEM.  The chain truncates (the tensor pipe rounds toward
+// zero), and at 10^5 streamed rows and more that is the largest error of the hi+lo variants: 512-step chunks are 6 %
+// faster, 128-step chunks 3-4 times more accurate (profiles/r2_error_growth_c5.log).  nbmf_opts.flush_interval or
+// NBMF_TP_CHUNK_STEPS override; otherwise the variants that carry a lo term (whose point is accuracy) take 128, the
+// hi-only variant (whose W_hi rounding error is larger anyway) 512.
+static void tp_set_chunk(const nbmf_handle *h, TPState *s)
+{
+    s->chunk_steps = h->opts.flush_interval > 0 ? h->opts.flush_interval : (h->path_mode == NBMF_PATH_TENSOR_FAST ? 512 : 128);
+    const char *env = getenv("NBMF_TP_CHUNK_STEPS");
+    if (env && atoi(env) > 0) s->chunk_steps = atoi(env);
+}
+
 // e5m2 lo part: rows of KP bytes, one box = 64 rows x KP bytes (one swizzle atom wide)
 static int make_map8(nbmf_handle *h, CUtensorMap *tm, void *base, int64_t rows, int KP)
 {
@@ -192,7 +207,7 @@ int tp_prepare(nbmf_handle *h)
     const int KP = h->Kc <= 64 ? 64 : 128;
     if (KP != h->Kp) { h->err = "internal: tensor KP != fp64 Kp"; return NBMF_ERR_STATE; }
     TPState *s = (TPState *)h->tp;
-    if (s && s->KP == KP) return NBMF_OK;
+    if (s && s->KP == KP) { tp_set_chunk(h, s); return NBMF_OK; }
     tp_free(h);
     s = new TPState();
     h->tp = s;
@@ -235,9 +250,7 @@ int tp_prepare(nbmf_handle *h)
         const long long v = atoll(sl);
         if (v > 1024) { uint32_t lim = (uint32_t)std::min<long long>(v, 0xffffffffll); cudaMemcpyToSymbol(c_tp_spin_limit, &lim, 4); }
     }
-    s->chunk_steps = h->opts.flush_interval > 0 ? h->opts.flush_interval : 512;
-    const char *env = getenv("NBMF_TP_CHUNK_STEPS");
-    if (env && atoi(env) > 0) s->chunk_steps = atoi(env);
+    tp_set_chunk(h, s);
     return NBMF_OK;
 }
 

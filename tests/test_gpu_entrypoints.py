@@ -163,39 +163,46 @@ def test_sample_gibbs_column_chain_matches_restatement_within_mc_error():
 @pytest.mark.parametrize("which", [0, 1])
 @pytest.mark.parametrize("shape", [1.0 / 128, 0.1, 0.5, 1.0, 3.7, 250.0, 262144.0])
 def test_device_gamma_draws_ks_and_moments(which, shape):
+    """Marsaglia-Tsang with the U^(1/a) boost for shape < 1 (gamma = 1/K priors with empty counts) up to counts of a
+    whole row of C5: Kolmogorov-Smirnov against SciPy's Gamma CDF and the first two moments.  For shape 1/128 half
+    a percent of the draws are below the smallest double; they sit at 0, where the CDF is 0.004."""
     from nbmf_b200 import Engine
     n = 200_000
     e = Engine()
     x = e.rng_probe(which, shape, 0.0, seed=17 + which, n=n)
     e.close()
     assert np.all(np.isfinite(x)) and np.all(x >= 0)
-    # moments: mean a, variance a
-    tol = 6.0 * np.sqrt(shape / n)
     rel32 = 3e-6 * shape if which == 1 else 0.0           # fp32 arithmetic of the fast sampler
-    assert abs(x.mean() - shape) < tol + rel32 + 1e-12, (x.mean(), shape)
-    assert abs(x.var() / shape - 1.0) < 0.05
-    if shape >= 0.1:                                       # for tiny shapes most of the mass underflows: test the log instead
-        d, p = st.kstest(x, "gamma", args=(shape,))
-        assert d < 0.006, (d, p)
-    else:
-        lx = np.log(np.maximum(x, 1e-300))
-        # E[log X] = digamma(a)
-        se = np.sqrt(sp.polygamma(1, shape) / n)
-        assert abs(lx[x > 1e-300].mean() - sp.digamma(shape)) < 8 * se + 0.6 * (x <= 1e-300).mean() * abs(sp.digamma(shape)) + 1e-9 or (x <= 1e-300).mean() > 0.01
+    assert abs(x.mean() - shape) < 6.0 * np.sqrt(shape / n) + rel32 + 1e-12, (x.mean(), shape)
+    # Var[sample variance] / sigma^4 = (kurtosis - 1) / n, kurtosis of Gamma(a) = 3 + 6 / a
+    assert abs(x.var() / shape - 1.0) < 5.0 * np.sqrt((2.0 + 6.0 / shape) / n) + 1e-3
+    d, _ = st.kstest(x, "gamma", args=(shape,))
+    assert d < (0.006 if shape >= 0.1 else 0.01), d
 
 
-@pytest.mark.parametrize("a,b", [(1.0, 1.0), (0.3, 2.5), (40.0, 3.0), (1.0 / 16, 1.0 / 16), (3000.0, 5000.0)])
+def _ks_logit_beta(t, a, b):
+    """KS distance between logit samples t and the logit of Beta(a, b); the upper tail through the survival
+    function of the mirrored variable, so that nothing is lost next to 1."""
+    t = np.sort(t)
+    n = t.size
+    sig = lambda z: 1.0 / (1.0 + np.exp(-z))
+    cdf = np.where(t <= 0, st.beta.cdf(sig(np.minimum(t, 0)), a, b), 1.0 - st.beta.cdf(sig(-np.maximum(t, 0)), b, a))
+    return max(np.max(np.arange(1, n + 1) / n - cdf), np.max(cdf - np.arange(0, n) / n))
+
+
+@pytest.mark.parametrize("a,b", [(1.0, 1.0), (0.3, 2.5), (40.0, 3.0), (1.0 / 16, 1.0 / 16), (1.0 / 128, 2.0), (3000.0, 5000.0)])
 def test_device_beta_draws_ks(a, b):
     from nbmf_b200 import Engine
     n = 200_000
     e = Engine()
     x = e.rng_probe(2, a, b, seed=23, n=n)
+    t = e.rng_probe(3, a, b, seed=23, n=n)
     e.close()
     assert np.all((x >= 0) & (x <= 1))
     m = a / (a + b)
     v = a * b / ((a + b) ** 2 * (a + b + 1))
     assert abs(x.mean() - m) < 6 * np.sqrt(v / n) + 2e-7
-    d, _ = st.kstest(x, "beta", args=(a, b))
+    d = _ks_logit_beta(t, a, b)
     assert d < 0.006, d
 
 

@@ -98,10 +98,17 @@ def test_auto_precision_selects_tensor_path_for_large_k():
     e.init_random_labels(64, 1)
     st = e.get_stats(64)
     W, H, _, _ = e.vb_aspect(64, iter=3)
-    e2 = Engine(precision=_lib.PREC_TENSOR)
+    path = e.timing()["path"]
+    # 3 updates at n = 1024: within the horizon of the e5m2-lo variant, beyond the hi-only one's
+    assert path == _lib.PATH_TENSOR_LO8
+    e2 = Engine(precision=_lib.PREC_TENSOR_LO8)
     e2.set_data(e.get_data()); e2.set_stats(*st)
     W2, H2, _, _ = e2.vb_aspect(64, iter=3)
     assert np.array_equal(W, W2) and np.array_equal(H, H2)   # same kernels, deterministic
+    # the reference's default, 100 updates, is beyond every f16 variant's horizon: the FP64 tensor pipe takes it
+    e.set_stats(*st)
+    e.vb_aspect(64, iter=100)
+    assert e.timing()["path"] == _lib.PATH_FP64
     # small K stays on the FP64 path even when asked for AUTO
     e.init_random_labels(8, 1)
     st8 = e.get_stats(8)
