@@ -61,6 +61,17 @@ def committed_traffic(workload, world, path):
 DTYPES = {0: "f64", 1: "f16 (streamed operand hi+lo in stage 2) / f32 accumulate in TMEM",
           2: "f16 (hi only) / f32 accumulate in TMEM",
           3: "f16 (streamed operand hi in f16 + lo in e5m2 in stage 2) / f32 accumulate in TMEM", 4: "f32"}
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """the one JSON line, on the real stdout"""
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(line), flush=True)
+
+
 METRIC = "vb_entries_K_per_s"
 UNIT = "entries*K/s"
 
@@ -182,7 +193,7 @@ def run_reference(args, wl):
                        "step": "one VB_aspect iteration: parameters, both statistics, ELBO (checklb=TRUE)"},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def bind_to_gpu_numa(local):
@@ -263,7 +274,7 @@ def run_gibbs(args, wl):
         dtc = max((t2 - t1) - (t1 - t0), 1e-9)
         line["cpu_baseline"] = {"value": Fs * Ns * K * 20 / dtc, "unit": UNIT, "cores": 1, "kind": "port",
                                 "sample": f"{Fs}x{Ns} columns of the same generator, 20 sweeps of Gibbs_DirBer_finite_Rcpp's collapsed sweep (oracle port, pinned draw for draw to the reference), 1 thread"}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -281,6 +292,11 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
+    # stdout carries ONE JSON line: whatever native libraries print there (NCCL's version banner, ...) goes to stderr
+    sys.stdout.flush()
+    global _REAL_STDOUT
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args, wl)
         return
@@ -432,7 +448,7 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             cb, _ = cpu_reference_run(wl, 3, 1, budget_s=20.0)
             line["cpu_baseline"] = cb
-        print(json.dumps(line), flush=True)
+        emit(line)
     eng.close()
     if world > 1:
         dist.destroy_process_group()

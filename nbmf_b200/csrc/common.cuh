@@ -56,6 +56,13 @@ struct nbmf_handle {
     int vb_K = 0, vb_iter = 0, vb_mean_params = 0;
     double vb_alpha = 1, vb_beta = 1, vb_gamma = 1;
 
+    // Row slicing of a sharded tensor-path session (library communicator only): the Dirichlet side is
+    // replicated data, but from the second iteration on each rank computes parameters, operand split and
+    // statistics for rows [row_lo, row_hi) only and the ranks exchange the f16 operands (all-gather); the
+    // fp64 arrays are made whole again by nbmf_vb_end
+    bool vb_sliced = false;
+    int64_t row_lo = 0, row_hi = 0;
+
     // contraction variant of the current session (nbmf_path), fixed by resolve_path()
     int path_mode = 0;
     int vb_horizon = 0;                          // VB updates planned from this start (AUTO precision)

@@ -1,6 +1,7 @@
 // host_common.h -- small host-side helpers shared by the translation units of libnbmf_cuda.
 #pragma once
 #include "common.cuh"
+#include <algorithm>
 
 #define CK(call) NBMF_CUDA_CHECK(h, call)
 #define LAUNCH_CHECK() CK(cudaGetLastError())
@@ -33,4 +34,13 @@ int nbmf_sum_ranks(nbmf_handle *h, void *buf, size_t count, int kind, cudaStream
 // maximum over the ranks of `count` uint64 values (operand exponents of the tensor path)
 int nbmf_max_ranks_u64(nbmf_handle *h, unsigned long long *buf, size_t count, cudaStream_t st);
 int nbmf_bcast_root(nbmf_handle *h, void *buf, size_t bytes, cudaStream_t st);
+// every rank owns rows [r * ceil(rows/G), ...) of `buf` (rows of row_bytes bytes): make the array whole on all ranks
+int nbmf_allgather_rows(nbmf_handle *h, void *buf, size_t row_bytes, int64_t rows_total, cudaStream_t st);
+// the row block of rank `rank` under that partition
+static inline void nbmf_row_block(int64_t rows_total, int world, int rank, int64_t *lo, int64_t *hi)
+{
+    const int64_t per = (rows_total + world - 1) / world;
+    *lo = std::min<int64_t>(rows_total, (int64_t)rank * per);
+    *hi = std::min<int64_t>(rows_total, *lo + per);
+}
 void nbmf_comm_release(nbmf_handle *h);   // destroys a communicator created by nbmf_comm_init_rank

@@ -239,12 +239,20 @@ __global__ void rows_to_colmajor_kernel(const double *__restrict__ src, int64_t 
 //    E_log_q_H_Rcpp :256-273).
 // One warp per row.
 // ---------------------------------------------------------------------------
-__global__ void params_rows_kernel(const double *__restrict__ statF, int64_t F, int K, int Kp,
-                                   double gamma, int mean_mode, int want_lb,
+__global__ void strided_copy_kernel(const double *__restrict__ src, int sstride, double *__restrict__ dst, int dstride, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[(size_t)i * dstride] = src[(size_t)i * sstride];
+}
+
+// rows [f0, F) are computed (f0 = first row of the launch); rows in [lb0, lb1) contribute to the prior
+// term of the ELBO (row-sliced sharded sessions sum that term over the ranks)
+__global__ void params_rows_kernel(const double *__restrict__ statF, int64_t f0, int64_t F, int K, int Kp,
+                                   double gamma, int mean_mode, int want_lb, int64_t lb0, int64_t lb1,
                                    double *__restrict__ A, double *__restrict__ EW, double *scal)
 {
     __shared__ double sh[32];
-    int64_t f = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int64_t f = f0 + (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     int lane = threadIdx.x & 31;
     double lb = 0.0, neg = 0.0;
     if (f < F) {
@@ -269,7 +277,7 @@ __global__ void params_rows_kernel(const double *__restrict__ statF, int64_t F, 
         if (want_lb) {
             sum_elw = warp_sum(sum_elw);
             q = warp_sum(q);
-            if (lane == 0)
+            if (lane == 0 && f >= lb0 && f < lb1)
                 lb = (lgamma(K * gamma) - K * lgamma(gamma)) + (gamma - 1.0) * sum_elw -
                      (lgamma(s) + q);
         }

@@ -690,17 +690,23 @@ static int run_pass(nbmf_handle *h, int owner_rows, double *sumlogD)
     return run_pass_simt(h, owner_rows, sumlogD, false);
 }
 
+// slice: 0 = every row; 1 = every row, but only the rank's own rows enter the ELBO's prior term (first iteration of a
+// row-sliced session: the statistics are still whole everywhere); 2 = the rank's own rows only
 static int run_params(nbmf_handle *h, int K, double alpha, double beta, double gamma, int mean_mode,
-                      int want_lb)
+                      int want_lb, int slice = 0)
 {
-    params_rows_kernel<<<nblk(h->F * 32, 256), 256, 0, h->stream>>>(h->statF, h->F, K, h->Kp, gamma,
-                                                                    mean_mode, want_lb, h->A, h->EW, h->scal);
-    LAUNCH_CHECK();
+    const int64_t f0 = slice == 2 ? h->row_lo : 0, f1 = slice == 2 ? h->row_hi : h->F;
+    const int64_t lb0 = slice ? h->row_lo : 0, lb1 = slice ? h->row_hi : h->F;
+    if (f1 > f0) {
+        params_rows_kernel<<<nblk((f1 - f0) * 32, 256), 256, 0, h->stream>>>(h->statF, f0, f1, K, h->Kp, gamma,
+                                                                             mean_mode, want_lb, lb0, lb1, h->A, h->EW, h->scal);
+        LAUNCH_CHECK();
+    }
     params_cols_kernel<<<nblk(h->N * 32, 256), 256, 0, h->stream>>>(h->statN, h->N, K, h->Kp, alpha, beta,
                                                                     mean_mode, want_lb, h->BB, h->EH, h->scal);
     LAUNCH_CHECK();
     h->timing.launches += 2;
-    if (use_tensor_path(h)) return tp_convert_operands(h);
+    if (use_tensor_path(h)) return tp_convert_operands(h, slice == 2);
     return NBMF_OK;
 }
 
@@ -723,6 +729,11 @@ extern "C" int nbmf_vb_begin(nbmf_handle *h, int K, double alpha, double beta, d
         if (rc) return rc;
     }
     h->xchg_timed = false;
+    // row slicing: library communicator + tensor path (NBMF_ROW_SLICING=0 keeps the row side replicated)
+    static const bool slicing_on = [] { const char *v = getenv("NBMF_ROW_SLICING"); return !(v && atoi(v) == 0); }();
+    h->vb_sliced = slicing_on && h->comm != nullptr && h->comm_world > 1 && use_tensor_path(h);
+    h->row_lo = 0; h->row_hi = h->F;
+    if (h->vb_sliced) nbmf_row_block(h->F, h->comm_world, h->comm_rank, &h->row_lo, &h->row_hi);
     h->vb_active = true; h->vb_K = K; h->vb_iter = 0; h->vb_mean_params = mean_params;
     h->vb_alpha = alpha; h->vb_beta = beta; h->vb_gamma = gamma;
     h->timing = nbmf_timing{};
@@ -751,8 +762,12 @@ extern "C" int nbmf_vb_step(nbmf_handle *h, int checklb)
     int rc;
     if (checklb) CK(cudaMemsetAsync(h->scal, 0, 3 * sizeof(double), h->stream)); // SUMLOGD, PRIOR_ROWS, PRIOR_COLS
     CK(cudaEventRecord(h->ev[1], h->stream));
-    if ((rc = run_params(h, h->vb_K, h->vb_alpha, h->vb_beta, h->vb_gamma, h->vb_mean_params, checklb))) return rc;
+    if ((rc = run_params(h, h->vb_K, h->vb_alpha, h->vb_beta, h->vb_gamma, h->vb_mean_params, checklb,
+                         h->vb_sliced ? (i == 0 ? 1 : 2) : 0))) return rc;
     CK(cudaEventRecord(h->ev[2], h->stream));
+    // row-sliced session: E_W exists in row blocks spread over the ranks from the second iteration on (a collective:
+    // the condition must not depend on which buffers this rank was given)
+    if (h->early_iter == i && h->vb_sliced && i > 0 && (rc = nbmf_allgather_rows(h, h->EW, (size_t)h->Kp * 8, h->F, h->stream))) return rc;
     if (h->early_iter == i && (h->early_EW || h->early_EH)) {
         // E_W / E_H of the call are the parameters at the top of its LAST iteration
         // (collapsed_gibbs_z_VB.cpp:507-514): final as soon as that iteration's parameter kernels
@@ -819,6 +834,25 @@ extern "C" int nbmf_vb_end(nbmf_handle *h, double *E_W, double *E_H, double *low
     if (!h) return NBMF_ERR_ARG;
     if (!h->vb_active) return fail(h, NBMF_ERR_STATE, "nbmf_vb_begin not called");
     CK(cudaSetDevice(h->device));
+    if (h->vb_sliced && h->vb_iter > 0) {
+        // row-sliced session: make the replicated fp64 arrays whole again (every rank holds its own rows of the
+        // statistics, and -- from the second iteration on -- of the parameters), and sum the ELBO's row term,
+        // which every rank accumulated over its own rows only, so that it is the replicated term callers expect
+        int rc0;
+        if ((rc0 = nbmf_allgather_rows(h, h->statF, (size_t)h->Kp * 8, h->F, h->stream))) return rc0;
+        if (h->vb_iter > 1) {
+            if ((rc0 = nbmf_allgather_rows(h, h->EW, (size_t)h->Kp * 8, h->F, h->stream))) return rc0;
+            if ((rc0 = nbmf_allgather_rows(h, h->A, (size_t)h->Kp * 8, h->F, h->stream))) return rc0;
+        }
+        const int n = std::min(h->vb_iter, h->lbs_cap);
+        if ((rc0 = ensure_stage(h, (size_t)n * 8))) return rc0;
+        strided_copy_kernel<<<nblk(n, 256), 256, 0, h->stream>>>(h->lbs + 1, 3, (double *)h->stage, 1, n);
+        LAUNCH_CHECK();
+        if ((rc0 = nbmf_sum_ranks(h, h->stage, (size_t)n, 0, h->stream))) return rc0;
+        strided_copy_kernel<<<nblk(n, 256), 256, 0, h->stream>>>((const double *)h->stage, 1, h->lbs + 1, 3, n);
+        LAUNCH_CHECK();
+    }
+    h->vb_sliced = false;
     CK(cudaEventRecord(h->ev[6], h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->vb_active = false;

@@ -149,6 +149,23 @@ int nbmf_bcast_root(nbmf_handle *h, void *buf, size_t bytes, cudaStream_t st)
     return NBMF_OK;
 }
 
+int nbmf_allgather_rows(nbmf_handle *h, void *buf, size_t row_bytes, int64_t rows_total, cudaStream_t st)
+{
+    if (!h->comm || h->comm_world <= 1) return NBMF_OK;
+    // blocks of unequal length (the last ranks may own fewer rows): one broadcast per owner, grouped
+    NCCLCK(h, ncclGroupStart());
+    for (int r = 0; r < h->comm_world; r++) {
+        int64_t lo, hi;
+        nbmf_row_block(rows_total, h->comm_world, r, &lo, &hi);
+        if (hi <= lo) continue;
+        char *p = (char *)buf + (size_t)lo * row_bytes;
+        ncclResult_t e = ncclBroadcast(p, p, (size_t)(hi - lo) * row_bytes, ncclChar, r, (ncclComm_t)h->comm, st);
+        if (e != ncclSuccess) { ncclGroupEnd(); h->err = std::string("ncclBroadcast: ") + ncclGetErrorString(e); return NBMF_ERR_CUDA; }
+    }
+    NCCLCK(h, ncclGroupEnd());
+    return NBMF_OK;
+}
+
 // ---------------------------------------------------------------------------
 // single-process group: one handle, one worker thread per device
 // ---------------------------------------------------------------------------

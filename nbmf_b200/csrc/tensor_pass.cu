@@ -102,8 +102,10 @@ bool tp_supported(const nbmf_handle *h, int K)
 static const double kHorizonLog2n[] = {14.0, 16.0, 18.0};            // n = 16384, 65536, 262144
 static const double kHorizon[2][3] = {
     // profiles/r2_error_growth_{16k,64k,c5}.log: last checkpoint (interpolated) with max(E_W, E_H) error <= 0.8e-5
-    {16, 23, 31},        // FAST (hi only), chunks of 512 steps
-    {64, 39, 57},        // LO8 (hi + e5m2 lo), chunks of 128 steps: the fp32 accumulation chain in TMEM is the other error source
+    // (one problem instance per size; 131072^2, tests/test_gpu_horizon.py, sits a little above the line between its
+    // neighbours, hence the margin on top of the 10 % of the interpolation)
+    {13, 17, 25},        // FAST (hi only), chunks of 512 steps
+    {55, 36, 50},        // LO8 (hi + e5m2 lo), chunks of 128 steps: the fp32 accumulation chain in TMEM is the other error source
 };
 
 static int tp_horizon(int variant /*0 FAST, 1 LO8*/, double n)
@@ -367,11 +369,32 @@ __global__ void tp_logcorr_kernel(const double *__restrict__ U, const __half *__
     if (threadIdx.x == 0) atomicAdd(sumlogD, t);
 }
 
+// the same with U - U_hi taken from the f16 lo part (exact to 2^-22 of U): a row-sliced session holds the fp64 A of
+// its own rows only, the f16 parts of all of them
+__global__ void tp_logcorr_lo_kernel(const __half *__restrict__ Ulo, const double *__restrict__ G, int64_t count, const int *dexp,
+                                     int which, double *sumlogD)
+{
+    __shared__ double sh[32];
+    const double inv = ldexp(1.0, -dexp[which]);
+    double t = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
+        t += (double)__half2float(Ulo[i]) * inv * G[i];
+    t = block_sum(t, sh);
+    if (threadIdx.x == 0) atomicAdd(sumlogD, t);
+}
+
 int tp_log_correction(nbmf_handle *h, int owner_rows, double *sumlogD)
 {
     TPState *s = (TPState *)h->tp;
     if (!s || !sumlogD) return NBMF_OK;
     const int64_t cnt = (owner_rows ? h->F : 2 * h->N) * (int64_t)s->KP;
+    if (owner_rows && h->vb_sliced) {
+        tp_logcorr_lo_kernel<<<(unsigned)std::min<int64_t>(2048, (cnt + 255) / 256), 256, 0, h->stream>>>(s->A_lo, h->GF, cnt, s->dexp, 0, sumlogD);
+        cudaError_t e0 = cudaGetLastError();
+        if (e0 != cudaSuccess) { h->err = std::string("tp_log_correction: ") + cudaGetErrorString(e0); return NBMF_ERR_CUDA; }
+        h->timing.launches += 1;
+        return NBMF_OK;
+    }
     tp_logcorr_kernel<<<(unsigned)std::min<int64_t>(2048, (cnt + 255) / 256), 256, 0, h->stream>>>(
         owner_rows ? h->A : h->BB, owner_rows ? s->A_hi : s->B_hi,
         owner_rows ? h->GF : h->GN, cnt, s->dexp, owner_rows ? 0 : 1, sumlogD);
@@ -394,7 +417,12 @@ int tp_finalize(nbmf_handle *h)
         }
         s->counts_ready = true;
     }
-    tp_finalize_kernel<<<(unsigned)((h->F * 32 + 255) / 256), 256, 0, h->stream>>>(h->A, h->GF, s->cntF, h->F, s->KP, h->statF);
+    {   // a row-sliced session finalises the rank's own rows only (the others' A is not current here)
+        const int64_t r0 = h->vb_sliced ? h->row_lo : 0, r1 = h->vb_sliced ? h->row_hi : h->F;
+        const int64_t o = r0 * (int64_t)s->KP;
+        if (r1 > r0)
+            tp_finalize_kernel<<<(unsigned)(((r1 - r0) * 32 + 255) / 256), 256, 0, h->stream>>>(h->A + o, h->GF + o, s->cntF + r0, r1 - r0, s->KP, h->statF + o);
+    }
     tp_finalize_kernel<<<(unsigned)((2 * h->N * 32 + 255) / 256), 256, 0, h->stream>>>(h->BB, h->GN, s->cntN, 2 * h->N, s->KP, h->statN);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { h->err = std::string("tp_finalize: ") + cudaGetErrorString(e); return NBMF_ERR_CUDA; }
@@ -402,20 +430,35 @@ int tp_finalize(nbmf_handle *h)
     return NBMF_OK;
 }
 
-int tp_convert_operands(nbmf_handle *h)
+int tp_convert_operands(nbmf_handle *h, bool rows_sliced)
 {
     TPState *s = (TPState *)h->tp;
     if (!s) { h->err = "tp_convert_operands before tp_prepare"; return NBMF_ERR_STATE; }
-    const int64_t ca = h->F * (int64_t)s->KP, cb = 2 * h->N * (int64_t)s->KP;
+    const int KP = s->KP;
+    // rows of A this rank converts: all of them, or its own block of a row-sliced session
+    const int64_t r0 = rows_sliced ? h->row_lo : 0, r1 = rows_sliced ? h->row_hi : h->F;
+    const int64_t ca = (r1 - r0) * (int64_t)KP, cb = 2 * h->N * (int64_t)KP, oa = r0 * (int64_t)KP;
     cudaMemsetAsync(s->dmax, 0, 16, h->stream);
-    tp_max_kernel<<<(unsigned)std::min<int64_t>(1024, (ca + 255) / 256), 256, 0, h->stream>>>(h->A, ca, s->dmax);
+    if (ca > 0) tp_max_kernel<<<(unsigned)std::min<int64_t>(1024, (ca + 255) / 256), 256, 0, h->stream>>>(h->A + oa, ca, s->dmax);
     tp_max_kernel<<<(unsigned)std::min<int64_t>(1024, (cb + 255) / 256), 256, 0, h->stream>>>(h->BB, cb, s->dmax + 1);
+    if (rows_sliced) {   // the scale of A is the maximum over ALL rows (positive doubles order like their bit patterns)
+        int rc = nbmf_max_ranks_u64(h, s->dmax, 1, h->stream);
+        if (rc) return rc;
+    }
     tp_exp_kernel<<<1, 32, 0, h->stream>>>(s->dmax, s->dexp);
-    tp_split_kernel<<<(unsigned)((ca + 255) / 256), 256, 0, h->stream>>>(h->A, ca, s->dexp, 0, s->A_hi, s->A_lo, s->A_lo8);
+    if (ca > 0) tp_split_kernel<<<(unsigned)((ca + 255) / 256), 256, 0, h->stream>>>(h->A + oa, ca, s->dexp, 0, s->A_hi + oa, s->A_lo + oa, s->A_lo8 + oa);
     tp_split_kernel<<<(unsigned)((cb + 255) / 256), 256, 0, h->stream>>>(h->BB, cb, s->dexp, 1, s->B_hi, s->B_lo, s->B_lo8);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { h->err = std::string("tp_convert_operands: ") + cudaGetErrorString(e); return NBMF_ERR_CUDA; }
     h->timing.launches += 5;
+    if (rows_sliced) {
+        // the f16 operands of the other ranks' rows: hi always (both passes), lo for the ELBO correction and the
+        // hi+lo variant, the e5m2 copy for the LO8 variant -- 2 + 2 (+ 1) bytes per element instead of the 8 of A
+        int rc;
+        if ((rc = nbmf_allgather_rows(h, s->A_hi, (size_t)KP * 2, h->F, h->stream))) return rc;
+        if ((rc = nbmf_allgather_rows(h, s->A_lo, (size_t)KP * 2, h->F, h->stream))) return rc;
+        if (h->path_mode == NBMF_PATH_TENSOR_LO8 && (rc = nbmf_allgather_rows(h, s->A_lo8, (size_t)KP, h->F, h->stream))) return rc;
+    }
     return NBMF_OK;
 }
 

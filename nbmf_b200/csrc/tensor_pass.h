@@ -8,7 +8,7 @@ bool tp_supported(const nbmf_handle *h, int K);   // K, sizes and device fit the
 // updates at this size (NBMF_PATH_FP64 if no tensor variant does)
 int tp_auto_mode(const nbmf_handle *h, int K, int horizon);
 int tp_prepare(nbmf_handle *h);               // allocate f16 operand buffers + tensor maps
-int tp_convert_operands(nbmf_handle *h);      // A, BB (fp64) -> scaled f16 hi/lo
+int tp_convert_operands(nbmf_handle *h, bool rows_sliced = false);   // rows_sliced: own rows of A only, then all-gather of the f16 parts      // A, BB (fp64) -> scaled f16 hi/lo
 int tp_pass(nbmf_handle *h, int owner_rows, double *sumlogD);
 // both passes, column block by column block behind the events of a pipelined upload
 int tp_passes_pipelined(nbmf_handle *h, int n_blocks, const int64_t *n0, cudaEvent_t *ev,
