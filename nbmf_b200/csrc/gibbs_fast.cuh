@@ -17,22 +17,26 @@
 //   * single pass: the K running sums c_k are kept in registers, the draw is #{k : c_k <= u c_K}
 //   * row-side counts: the lane owns its row, so its histogram is a private shared-memory column (no
 //     shared-memory atomics) that leaves once per block as one integer atomic per (row, label);
-//   * column-side counts: the 2K (label, bit) keys of the 32 entries are counted with ballots, lane j
-//     keeping key j; the eight warps' byte counts are summed and leave as plain stores into the
-//     row tile's partial buffer cNp [f tiles][2N][KT], which gibbs_draw_kernel totals.
+//   * column-side counts: every entry leaves its (label, bit) key as a byte in a shared-memory tile; after a
+//     barrier the block turns by 90 degrees -- thread = column (x row group) -- and counts its column's keys in
+//     a private shared-memory histogram column (bank = thread, no atomics).  [The first version counted with
+//     2K ballots per warp and column: 128 of its ~210 warp instructions per 32 entries at K = 16.]  The totals
+//     leave as plain stores into the row tile's partial buffer cNp [f tiles][2N][KT], which gibbs_draw_kernel
+//     sums, or as integer atomics when there are many row tiles.
 // Integer counts only, so the result does not depend on the order of the atomics.
 #pragma once
 #include "common.cuh"
 
 #define GIBBS_NB(KT) ((KT) <= 16 ? 128 : 64)   // columns per sub-tile
-#define GIBBS_FB 256          // rows per tile (8 warps x 32)
+#define GIBBS_WMAX 8          // warps per block (rows per tile = 32 x warps; the launch picks 4..8 to fit F)
 #define GIBBS_CT_MAX 8        // sub-tiles per block (row counts of a block fit 16 bits)
 template <int KT> struct GibbsSmem {
-    static constexpr int NB = GIBBS_NB(KT), KEYS = 2 * KT;
-    static constexpr size_t H_BYTES = (size_t)2 * NB * KT * 4;     // float  sH[2][NB][KT]
-    static constexpr size_t F_BYTES = (size_t)8 * KT * 32 * 2;     // ushort hF[8][KT][32]
-    static constexpr size_t N_BYTES = (size_t)NB * KEYS * 8;       // uchar  hN[NB][KEYS][8]
-    static constexpr size_t BYTES = H_BYTES + F_BYTES + N_BYTES;
+    static constexpr int NB = GIBBS_NB(KT), KEYS = 2 * KT, ROWS = 32 * GIBBS_WMAX;
+    static constexpr size_t H_BYTES = (size_t)2 * NB * KT * 4;          // float  sH[2][NB][KT]
+    static constexpr size_t F_BYTES = (size_t)GIBBS_WMAX * KT * 32 * 2; // ushort hF[warp][KT][32]
+    static constexpr size_t K_BYTES = (size_t)NB * ROWS;                // uchar  sK[NB][ROWS]: key of (column, row), 0xFF = none
+    static constexpr size_t C_BYTES = (size_t)KEYS * ROWS * 4;          // uint   hC[KEYS][thread]
+    static constexpr size_t BYTES = H_BYTES + F_BYTES + K_BYTES + C_BYTES;
 };
 
 // float uniform in (0,1): 23 bits + 1/2, exactly representable, so it is never 0 and never rounds to 1
@@ -221,22 +225,30 @@ struct GibbsSweepArgs {
 };
 
 template <int KT>
-__global__ void __launch_bounds__(256) gibbs_sweep_kt_kernel(GibbsSweepArgs a)
+__global__ void __launch_bounds__(32 * GIBBS_WMAX) gibbs_sweep_kt_kernel(GibbsSweepArgs a)
 {
     static_assert(KT == 4 || KT == 8 || KT == 16 || KT == 32, "KT");
     constexpr int KEYS = 2 * KT;                          // (label, bit) keys: key = 2 label + bit
-    constexpr int NB = GIBBS_NB(KT);
+    constexpr int NB = GIBBS_NB(KT), ROWS = 32 * GIBBS_WMAX;
     extern __shared__ __align__(16) unsigned char gsm[];
     float (*sH)[NB][KT] = reinterpret_cast<float (*)[NB][KT]>(gsm);                                  // [bit][column][k] Beta factors
     unsigned short (*hF)[KT][32] = reinterpret_cast<unsigned short (*)[KT][32]>(gsm + GibbsSmem<KT>::H_BYTES);   // [warp][k][lane] private row histograms
-    unsigned char (*hN)[KEYS][8] = reinterpret_cast<unsigned char (*)[KEYS][8]>(gsm + GibbsSmem<KT>::H_BYTES + GibbsSmem<KT>::F_BYTES);   // [column][key][warp]
+    unsigned char (*sK)[ROWS] = reinterpret_cast<unsigned char (*)[ROWS]>(gsm + GibbsSmem<KT>::H_BYTES + GibbsSmem<KT>::F_BYTES);
+    uint32_t (*hC)[ROWS] = reinterpret_cast<uint32_t (*)[ROWS]>(gsm + GibbsSmem<KT>::H_BYTES + GibbsSmem<KT>::F_BYTES + GibbsSmem<KT>::K_BYTES);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int64_t fw = (int64_t)blockIdx.y * 8 + warp;    // bit word (32 rows) of this warp
+    const int nwarps = blockDim.x >> 5, nthreads = blockDim.x;
+    const int64_t fw = (int64_t)blockIdx.y * nwarps + warp;   // bit word (32 rows) of this warp
     const int64_t f = fw * 32 + lane;
     const bool row_ok = f < a.F;
     const bool word_ok = fw * 32 < a.F;                   // warp-uniform
+    // phase 2 geometry: thread = (column, row group); a group covers `gwords` 4-row words of the key tile
+    const int groups = nthreads / NB > 0 ? nthreads / NB : 1;
+    const int gwords = (8 * nwarps + groups - 1) / groups;
+    const int p2col = tid % NB, p2grp = tid / NB;
+    const bool p2_on = tid < NB * groups;
 #pragma unroll
     for (int k = 0; k < KT; k++) hF[warp][k][lane] = 0;
+    for (int i = tid; i < KEYS * ROWS; i += nthreads) (&hC[0][0])[i] = 0;
     float w[KT];
 #pragma unroll
     for (int k4 = 0; k4 < KT; k4 += 4) {
@@ -247,28 +259,31 @@ __global__ void __launch_bounds__(256) gibbs_sweep_kt_kernel(GibbsSweepArgs a)
         const int64_t n0 = ((int64_t)blockIdx.x * a.ct + st) * NB;
         if (n0 >= a.N) break;                             // block-uniform
         const int nb = (int)min((int64_t)NB, a.N - n0);
-        __syncthreads();                                  // the previous sub-tile's tables and counts are consumed
-        for (int i = tid; i < 2 * NB * KT; i += 256) {
+        __syncthreads();                                  // the previous sub-tile's tables, keys and counts are consumed
+        for (int i = tid; i < 2 * NB * KT; i += nthreads) {
             const int tb = i / (NB * KT), r = (i / KT) % NB, k = i % KT;
             sH[tb][r][k] = (r < nb) ? a.HH[((int64_t)tb * a.N + n0 + r) * KT + k] : 0.f;
         }
-        if (!word_ok)                                     // a warp beyond F still owns its slice of the staging array
-            for (int i = lane; i < NB * KEYS; i += 32) hN[i / KEYS][i % KEYS][warp] = 0;
         __syncthreads();
-        if (word_ok) {
-            for (int j0 = 0; j0 < nb; j0 += 4) {
-                // one Philox block per four consecutive GLOBAL columns (keyed by the global column, so the
-                // chain does not depend on the sharding); a misaligned shard start straddles two blocks
-                const int64_t ng0 = n0 + j0 + a.n_offset;
-                const uint32_t k1 = (uint32_t)(a.seed >> 32) ^ 0x2545F491u;
-                const philox4 ra = philox4x32_10((uint32_t)f, (uint32_t)(ng0 >> 2), (uint32_t)(ng0 >> 34), a.sweep, (uint32_t)a.seed, k1);
-                philox4 rb4 = ra;
-                const int mis = (int)(ng0 & 3);           // warp-uniform
+        // ---- phase 1: thread = row, loop over the sub-tile's columns
+        for (int j0 = 0; j0 < nb; j0 += 4) {
+            // one Philox block per four consecutive GLOBAL columns (keyed by the global column, so the
+            // chain does not depend on the sharding); a misaligned shard start straddles two blocks
+            const int64_t ng0 = n0 + j0 + a.n_offset;
+            const uint32_t k1 = (uint32_t)(a.seed >> 32) ^ 0x2545F491u;
+            philox4 ra, rb4;
+            const int mis = (int)(ng0 & 3);               // warp-uniform
+            if (word_ok) {
+                ra = philox4x32_10((uint32_t)f, (uint32_t)(ng0 >> 2), (uint32_t)(ng0 >> 34), a.sweep, (uint32_t)a.seed, k1);
+                rb4 = ra;
                 if (mis) rb4 = philox4x32_10((uint32_t)f, (uint32_t)((ng0 >> 2) + 1), (uint32_t)(((ng0 >> 2) + 1) >> 32), a.sweep, (uint32_t)a.seed, k1);
+            }
 #pragma unroll
-                for (int jj = 0; jj < 4; jj++) {
-                    const int j = j0 + jj;
-                    if (j >= nb) break;                   // warp-uniform
+            for (int jj = 0; jj < 4; jj++) {
+                const int j = j0 + jj;
+                if (j >= nb) break;                       // block-uniform
+                int key = 0xFF;
+                if (word_ok) {
                     const int64_t n = n0 + j;
                     const uint32_t vw = __ldg(a.vc + n * a.Fw + fw);
                     const uint32_t mw = a.mc ? __ldg(a.mc + n * a.Fw + fw) : 0xffffffffu;
@@ -296,24 +311,32 @@ __global__ void __launch_bounds__(256) gibbs_sweep_kt_kernel(GibbsSweepArgs a)
 #pragma unroll
                     for (int k = 0; k < KT - 1; k++) kz += (c[k] <= target) ? 1 : 0;
                     kz = min(kz, a.K - 1);
-                    if (obs) hF[warp][kz][lane] += 1;
+                    if (obs) { hF[warp][kz][lane] += 1; key = 2 * kz + v; }
                     if (a.Zout && row_ok) a.Zout[f + a.F * n] = obs ? kz : NBMF_NA_INTEGER;
-                    const int key = obs ? 2 * kz + v : -1;
+                }
+                sK[j][tid] = (unsigned char)key;
+            }
+        }
+        __syncthreads();
+        // ---- phase 2: thread = (column, row group): the column's keys into the thread's private histogram column
+        if (p2_on && p2col < nb) {
+            const uint32_t *kw = reinterpret_cast<const uint32_t *>(&sK[p2col][0]);
+            const int w0 = p2grp * gwords, w1 = min(8 * nwarps, w0 + gwords);
+            for (int q = w0; q < w1; q++) {
+                const uint32_t kk = kw[q];
 #pragma unroll
-                    for (int kk = 0; kk < KEYS; kk++) {
-                        const uint32_t b = __ballot_sync(0xffffffffu, key == kk);
-                        if ((kk & 31) == lane) hN[j][kk][warp] = (unsigned char)__popc(b);
-                    }
+                for (int b = 0; b < 4; b++) {
+                    const uint32_t key = (kk >> (8 * b)) & 0xFFu;
+                    if (key != 0xFFu) hC[key][tid] += 1;
                 }
             }
         }
         __syncthreads();
-        // column-side counts of the sub-tile: sum over the eight warps, out to (2n + bit, label)
-        for (int i = tid; i < nb * KEYS; i += 256) {
-            const int j = i / KEYS, kk = i % KEYS;
-            const uint2 q = *reinterpret_cast<const uint2 *>(&hN[j][kk][0]);
-            const uint32_t s2 = __vadd4(q.x, q.y);        // bytewise (each at most 64)
-            const int cnt = (int)((s2 & 0xff) + ((s2 >> 8) & 0xff) + ((s2 >> 16) & 0xff) + (s2 >> 24));
+        // column-side counts of the sub-tile: sum over the row groups, out to (2n + bit, label); clear for the next one
+        for (int i = tid; i < nb * KEYS; i += nthreads) {
+            const int j = i % nb, kk = i / nb;            // consecutive threads: consecutive columns (bank = column)
+            int cnt = 0;
+            for (int g = 0; g < groups; g++) { cnt += (int)hC[kk][g * NB + j]; hC[kk][g * NB + j] = 0; }
             const int64_t idx = (2 * (n0 + j) + (kk & 1)) * KT + (kk >> 1);
             if (a.cn_atomic) { if (cnt) atomicAdd(a.cNp + idx, cnt); }
             else a.cNp[(int64_t)blockIdx.y * 2 * a.N * KT + idx] = cnt;

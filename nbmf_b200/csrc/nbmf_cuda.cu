@@ -1231,11 +1231,11 @@ extern "C" int nbmf_vb_dirber(nbmf_handle *h, int K, double alpha, double beta, 
 // Gibbs
 // ---------------------------------------------------------------------------
 template <int KT>
-static cudaError_t launch_gibbs_sweep(const GibbsSweepArgs &a, dim3 grid, cudaStream_t st)
+static cudaError_t launch_gibbs_sweep(const GibbsSweepArgs &a, dim3 grid, int warps, cudaStream_t st)
 {
     cudaError_t e = cudaFuncSetAttribute(gibbs_sweep_kt_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GibbsSmem<KT>::BYTES);
     if (e != cudaSuccess) return e;
-    gibbs_sweep_kt_kernel<KT><<<grid, 256, GibbsSmem<KT>::BYTES, st>>>(a);
+    gibbs_sweep_kt_kernel<KT><<<grid, 32 * warps, GibbsSmem<KT>::BYTES, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -1250,7 +1250,18 @@ static int gibbs_dirber_fast(nbmf_handle *h, int K, double alpha, double beta, d
     const int64_t F = h->F, N = h->N;
     const int KT = K <= 4 ? 4 : K <= 8 ? 8 : K <= 16 ? 16 : 32;
     const size_t fk = (size_t)F * K, nk = (size_t)N * K, fkt = (size_t)F * KT, nkt = (size_t)N * KT;
-    const int f_tiles = (int)((F + GIBBS_FB - 1) / GIBBS_FB);
+    // rows per tile = 32 x warps per block: 4..8 warps, whichever leaves the fewest idle warps in the last tile
+    // (MNIST: 784 rows = 25 bit words -> 5 warps x 5 tiles)
+    const int64_t f_words = (F + 31) / 32;
+    int warps = GIBBS_WMAX;
+    {
+        int64_t best = -1;
+        for (int w = GIBBS_WMAX; w >= 4; w--) {
+            const int64_t waste = (f_words + w - 1) / w * w - f_words;
+            if (best < 0 || waste < best) { best = waste; warps = w; }
+        }
+    }
+    const int f_tiles = (int)((f_words + warps - 1) / warps);
     // column-side counts: per-row-tile partial buffers (plain stores) while they stay small, integer atomics beyond
     const bool cn_atomic = f_tiles > 16;
     DevBuf<int32_t> cF, cN, cNp, Zd;
@@ -1328,10 +1339,10 @@ static int gibbs_dirber_fast(nbmf_handle *h, int K, double alpha, double beta, d
         sw.sweep = (uint32_t)i; sw.Zout = (i == iter - 1) ? (int32_t *)Zd : nullptr;
         cudaError_t e;
         switch (KT) {
-        case 4: e = launch_gibbs_sweep<4>(sw, sgrid, h->stream); break;
-        case 8: e = launch_gibbs_sweep<8>(sw, sgrid, h->stream); break;
-        case 16: e = launch_gibbs_sweep<16>(sw, sgrid, h->stream); break;
-        default: e = launch_gibbs_sweep<32>(sw, sgrid, h->stream); break;
+        case 4: e = launch_gibbs_sweep<4>(sw, sgrid, warps, h->stream); break;
+        case 8: e = launch_gibbs_sweep<8>(sw, sgrid, warps, h->stream); break;
+        case 16: e = launch_gibbs_sweep<16>(sw, sgrid, warps, h->stream); break;
+        default: e = launch_gibbs_sweep<32>(sw, sgrid, warps, h->stream); break;
         }
         CK(e);
         parts_valid = true;

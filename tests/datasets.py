@@ -20,6 +20,14 @@ def mnistbinary_2000():
     return np.asfortranarray(bits.T.astype(np.int32))
 
 
+def mnistbinary_full():
+    """all of data/mnistbinary: 784 x 60000 (BASELINE configs[2] at its size)"""
+    d = np.load(os.path.join(HERE, "mnistbinary_full.npz"))
+    F, N = (int(x) for x in d["shape"])
+    bits = np.unpackbits(d["bits"], axis=1, bitorder="little")[:, :F]
+    return np.asfortranarray(bits.T.astype(np.int32))
+
+
 def hold_out(V, frac, seed):
     """BASELINE config 2: hide `frac` of the observed entries (the experiments use
     runif(1) > 0.75, fig10:57; BASELINE.json says 20 %).  Returns (train, test)."""

@@ -18,8 +18,8 @@ def _pack_cols(V):
     return np.packbits(pad.T.reshape(N, fw, 32), axis=2, bitorder="little").view(np.uint32).reshape(N, fw)
 
 
-@pytest.mark.parametrize("F,N,K,blk,prec", [(512, 1024, 64, 256, 2), (640, 768, 40, 128, 2), (512, 2048, 128, 512, 3),
-                                             (384, 1000, 64, 256, 2)])
+@pytest.mark.parametrize("F,N,K,blk,prec", [(512, 1024, 64, 256, 2), (640, 768, 40, 128, 2), (512, 2048, 128, 512, 4),
+                                             (384, 1000, 64, 256, 4)])
 def test_pipelined_call_matches_staged_calls_and_oracle(F, N, K, blk, prec):
     from nbmf_b200 import Engine
     V, _, _ = oracle.generate(F, N, 4, 0.8, 0.8, 11)
@@ -34,17 +34,18 @@ def test_pipelined_call_matches_staged_calls_and_oracle(F, N, K, blk, prec):
     W0, H0, lb0, _ = e0.vb_aspect(K, 1.0, 1.0, 0.5, iter=iters, checklb=True)
     e1 = Engine(precision=prec, pipe_block_cols=blk)
     W1, H1, lb1 = e1.vb_aspect_bits(bits, F, N, K, stats, 1.0, 1.0, 0.5, iter=iters, checklb=True)
-    assert np.allclose(W1, W0, rtol=2e-5, atol=1e-12) and np.allclose(H1, H0, rtol=2e-5, atol=1e-12)
+    # the pipelined call cuts the reductions into other chunks than the staged one: same arithmetic, other fp32 chains
+    relF = lambda a, b: np.linalg.norm(a - b) / np.linalg.norm(b)
+    assert relF(W1, W0) < 2e-6 and relF(H1, H0) < 2e-6
     assert np.allclose(lb1, lb0, rtol=1e-6)
     # a second call on the same handle (buffers reused, same shape) gives the same answer
     W2, H2, lb2 = e1.vb_aspect_bits(bits, F, N, K, stats, 1.0, 1.0, 0.5, iter=iters, checklb=True)
-    assert np.allclose(W2, W1, rtol=1e-6, atol=1e-12) and np.allclose(lb2, lb1, rtol=1e-7)
+    assert np.array_equal(W2, W1) and np.array_equal(H2, H1) and np.array_equal(lb2, lb1)
     # and the oracle
     o = oracle.vb_aspect(V, Z, K, 1.0, 1.0, 0.5, iter=iters, checklb=True)
     Wo, Ho, lbo = o["E_W"], o["E_H"], o["lowerbounds"]
-    tol = 2e-4 if prec == 3 else 5e-5
-    assert np.linalg.norm(W1 - Wo) / np.linalg.norm(Wo) < tol
-    assert np.linalg.norm(H1 - Ho) / np.linalg.norm(Ho) < tol
+    tol = 1e-5      # the north star's gate, norm-wise (hi+lo variants; the hi-only one is for 10^4 rows and more)
+    assert relF(W1, Wo) < tol and relF(H1, Ho) < tol, (relF(W1, Wo), relF(H1, Ho))
     assert abs(lb1[-1] - lbo[-1]) / abs(lbo[-1]) < 1e-5
 
 
