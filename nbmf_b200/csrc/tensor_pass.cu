@@ -62,6 +62,7 @@ struct TPState {
     double *cntF = nullptr, *cntN = nullptr; // exact observed counts per owner lane: [F], [2N]
     bool counts_ready = false;
     int chunk_steps = 32;
+    int sub_steps = 0;
 };
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -174,16 +175,20 @@ static int make_map(nbmf_handle *h, CUtensorMap *tm, void *base, int64_t rows, i
     return NBMF_OK;
 }
 
-// Steps per chunk = length of an fp32 accumulation chain in TMEM.  The chain truncates (the tensor pipe rounds toward
-// zero), and at 10^5 streamed rows and more that is the largest error of the hi+lo variants: 512-step chunks are 6 %
-// faster, 128-step chunks 3-4 times more accurate (profiles/r2_error_growth_c5.log).  nbmf_opts.flush_interval or
-// NBMF_TP_CHUNK_STEPS override; otherwise the variants that carry a lo term (whose point is accuracy) take 128, the
-// hi-only variant (whose W_hi rounding error is larger anyway) 512.
+// Two lengths.  chunk_steps = steps per work item (one owner tile x one chunk of the streamed operand): long items amortise
+// the owner-operand reload and the refill of the S -> R -> G pipeline and keep the partial buffers small.  sub_steps =
+// length of an fp32 accumulation chain in TMEM: the tensor pipe truncates, and at 10^5 streamed rows and more the chain
+// is the largest error of the hi+lo variants (profiles/r2_error_growth_c5.log: 128-step chains are 3-4 times more
+// accurate than 512-step ones), so G is folded into the item's partial every sub_steps steps -- the stage-2 issuer
+// pauses for one TMEM read, stage 1 and the epilogue run on.  nbmf_opts.flush_interval sets sub_steps;
+// NBMF_TP_CHUNK_STEPS / NBMF_TP_SUB_STEPS override (sub >= chunk: one chain per item).
 static void tp_set_chunk(const nbmf_handle *h, TPState *s)
 {
-    s->chunk_steps = h->opts.flush_interval > 0 ? h->opts.flush_interval : (h->path_mode == NBMF_PATH_TENSOR_FAST ? 512 : 128);
-    const char *env = getenv("NBMF_TP_CHUNK_STEPS");
-    if (env && atoi(env) > 0) s->chunk_steps = atoi(env);
+    s->chunk_steps = 512;
+    s->sub_steps = h->opts.flush_interval > 0 ? h->opts.flush_interval : 128;
+    if (const char *env = getenv("NBMF_TP_CHUNK_STEPS")) if (atoi(env) > 0) s->chunk_steps = atoi(env);
+    if (const char *env = getenv("NBMF_TP_SUB_STEPS")) if (atoi(env) >= 0) s->sub_steps = atoi(env);
+    if (s->sub_steps > 0 && s->sub_steps < 4) s->sub_steps = 4;
 }
 
 // e5m2 lo part: rows of KP bytes, one box = 64 rows x KP bytes (one swizzle atom wide)
@@ -658,6 +663,8 @@ struct TPArgs {
     int64_t owner_tiles, tile_begin, owner_tiles_total;
     int64_t step_begin, step_end;  // steps of 64 streamed rows
     int chunk_steps, n_chunks, chunk_base;
+    int sub_steps;                 // length of an fp32 accumulation chain in TMEM: G is folded into the item's partial
+                                   // every sub_steps steps (0 = once per item)
     int *item_ctr;                 // work queue: next item of this launch (zeroed by the host)
     float *partial;                // [chunks of all launches][owner_tiles_total*128][KP]
     const int *dexp;               // eA, eB
@@ -706,7 +713,7 @@ struct TPCfg {
     static_assert(COL_U + KP / 2 + (LO8 ? 16 * NR : 0) <= 512, "TMEM columns");
     static constexpr int SMEM_BYTES = STAGES * TILE_BYTES + 1024 /*align*/ + 512 /*barriers*/;
     static_assert(TILE_BYTES % 1024 == 0, "stage alignment (SWIZZLE_128B atoms)");
-    static_assert(2 * STAGES + NS + 3 * NR + 2 + 8 <= 64, "barrier area");
+    static_assert(2 * STAGES + NS + 3 * NR + 3 + 8 <= 64, "barrier area");
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory");
 };
 
@@ -728,7 +735,8 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
     const uint32_t BAR_RREADY = BAR_SFREE + 8u * C::NS;               // [NR] epilogue has written R (128 arrivals)
     const uint32_t BAR_RFREE = BAR_RREADY + 8u * C::NR;               // [NR] stage 2 done           (commit)
     const uint32_t BAR_GFULL = BAR_RFREE + 8u * C::NR;
-    const uint32_t BAR_UREADY = BAR_GFULL + 8;
+    const uint32_t BAR_GDRAIN = BAR_GFULL + 8;                        // G folded into the partial inside an item (512 arrivals)
+    const uint32_t BAR_UREADY = BAR_GDRAIN + 8;
     // Work items come from a global counter (one atomicAdd per item by the producer thread) and
     // reach the other roles through a 4-entry ring: CTAs that start late -- e.g. because the
     // exchange's NCCL kernel holds their SM for the first millisecond -- simply take fewer items.
@@ -747,6 +755,7 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
         for (int s = 0; s < C::NS; s++) mbar_init(BAR_SFREE + 8u * s, 128);
         for (int s = 0; s < C::NR; s++) { mbar_init(BAR_SFULL + 8u * s, 1); mbar_init(BAR_RREADY + 8u * s, 128); mbar_init(BAR_RFREE + 8u * s, 1); }
         mbar_init(BAR_GFULL, 1);
+        mbar_init(BAR_GDRAIN, 512);
         mbar_init(BAR_UREADY, 512);
         for (int s = 0; s < 4; s++) { mbar_init(BAR_IFULL + 8u * s, 1); mbar_init(BAR_IEMPTY + 8u * s, 2 + 512); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -877,7 +886,7 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
             constexpr uint32_t DLO2 = ((uint32_t)C::BLOCK_BYTES >> 4) << 16; // MN-major: LBO = k-block stride
             uint32_t g_stage = 0;                // smem ring position of the next tile to run stage 2 on
             uint32_t gs = 0;                     // global step counter
-            uint32_t u_phase = 0, item_no = 0;
+            uint32_t u_phase = 0, item_no = 0, gd_phase = 0;
             PROF_DECL;
             for (int64_t w; (w = take_item(item_no, 13)) >= 0;) {
                 const int chunk = (int)(w / a.owner_tiles);
@@ -888,9 +897,19 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
                 u_phase ^= 1;
                 bool ok = true;
                 uint32_t pre = 0;
+                int next_fold = a.sub_steps > 0 ? a.sub_steps : 0x7fffffff;   // first step of the next accumulation chain
                 PROF_ACC(0);
                 for (int t = 0; t < nst; t++) {
                     const uint32_t rs = gs & 3u;
+                    bool fresh = (t == 0);
+                    if (t == next_fold) {
+                        // the chain that ended with step t-1 has been handed to the epilogue (commit below); G may only be
+                        // overwritten once every epilogue group has folded it into the item's partial
+                        if (!mbar_wait(BAR_GDRAIN, gd_phase, abort_flag, 15)) { ok = false; break; }
+                        gd_phase ^= 1u;
+                        next_fold += a.sub_steps;
+                        fresh = true;
+                    }
                     if (!pre && !mbar_wait(BAR_RREADY + 8u * rs, (gs >> 2) & 1u, abort_flag, 4)) { ok = false; break; }
                     tc_fence_after();
                     PROF_ACC(1);
@@ -905,7 +924,7 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
 #pragma unroll
                     for (int j = 0; j < C::STEP_ROWS / 16; j++)
                         tc_mma_ts2(tmem + C::COL_G, rcol + j * 8, lo + ((j * (16 * 128)) >> 4), DHI, IDESC2,
-                                   (t == 0 && j == 0) ? 0u : 1u);
+                                   (fresh && j == 0) ? 0u : 1u);
                     if (USE_LO && !LO8) {
 #pragma unroll
                         for (int j = 0; j < C::STEP_ROWS / 16; j++)
@@ -927,6 +946,7 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
                     PROF_ACC(2);
                     tc_commit(empty);                // tile consumed: the smem stage goes back to the producer
                     tc_commit(BAR_RFREE + 8u * rs);  // ... and the R slot to the epilogue
+                    if (t + 1 == next_fold && t + 1 < nst) tc_commit(BAR_GFULL);   // end of a chain inside the item
                     PROF_ACC(3);
                 }
                 tc_commit(BAR_GFULL);
@@ -966,7 +986,9 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
         int64_t prev_w = -1;
         constexpr int GCOLS = 32;                            // G columns drained per group
         constexpr int NDRAIN = KP / GCOLS;                   // groups that take part (4 or 2)
-        auto drain_G = [&](int64_t pw) {
+        // G -> the item's fp32 partial.  fold: add to what earlier chains of the same item left there (same thread, same
+        // addresses, program order: deterministic; the 64 KB of an item stay in L2 between folds)
+        auto drain_G = [&](int64_t pw, bool fold) {
             if (grp < NDRAIN) {
                 const int pchunk = a.chunk_base + (int)(pw / a.owner_tiles);
                 const int64_t ptile = a.tile_begin + pw % a.owner_tiles;
@@ -975,10 +997,27 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
                 tc_ld32(tmem + lane_addr + C::COL_G + grp * GCOLS, r);
                 tc_wait_ld();
 #pragma unroll
-                for (int i = 0; i < 32; i += 4)
-                    *reinterpret_cast<uint4 *>(dst + i) = make_uint4(r[i], r[i + 1], r[i + 2], r[i + 3]);
+                for (int i = 0; i < 32; i += 4) {
+                    float4 v = make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+                    if (fold) {
+                        const float4 o = *reinterpret_cast<const float4 *>(dst + i);
+                        v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+                    }
+                    *reinterpret_cast<float4 *>(dst + i) = v;
+                }
             }
         };
+        // a chain ended inside the item: fold G into the partial and hand it back to the stage-2 issuer
+        auto fold_G = [&](int64_t pw, bool fold) -> bool {
+            if (!mbar_wait(BAR_GFULL, g_phase, abort_flag, 16)) return false;
+            g_phase ^= 1;
+            tc_fence_after();
+            drain_G(pw, fold);
+            tc_fence_before();
+            mbar_arrive(BAR_GDRAIN);
+            return true;
+        };
+        bool prev_folded = false;                   // the previous item left earlier chains in its partial
         uint32_t item_no = 0;
         for (int64_t w; ok && (w = take_item(item_no, 14)) >= 0;) {
             const int chunk = (int)(w / a.owner_tiles);
@@ -1003,7 +1042,7 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
                 ok = ok && mbar_wait(BAR_GFULL, g_phase, abort_flag, 7);
                 g_phase ^= 1;
                 tc_fence_after();
-                drain_G(prev_w);
+                drain_G(prev_w, prev_folded);
             }
             if (grp < KP / 32) {
                 tc_st16(tmem + lane_addr + C::COL_U + grp * 16, ur);
@@ -1034,8 +1073,14 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
                 if (HAS_NA) mp += 4 * WPS;
             };
             if (tfirst < nst) load_bits();
+            // accumulation chains of this item: [0, sub), [sub, 2 sub), ...; cur_chain = the one this group is in
+            const int sub = a.sub_steps > 0 ? a.sub_steps : 0x7fffffff;
+            const int n_chain = a.sub_steps > 0 ? (nst + sub - 1) / sub : 1;
+            int cur_chain = 0;
             PROF_ACC(0);
             for (int t = tfirst; t < nst && ok; t += 4) {
+                while (ok && t >= (cur_chain + 1) * sub) { ok = fold_G(w, cur_chain > 0); cur_chain++; }   // this group's steps of the chain are done
+                if (!ok) break;
                 uint32_t sel[WPS], vv[WPS];
 #pragma unroll
                 for (int i = 0; i < WPS; i++) {
@@ -1122,6 +1167,9 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
                 r_par ^= 1u;
                 PROF_ACC(6);
             }
+            // chains this group has no step beyond (short tail): every group takes part in every fold
+            while (ok && cur_chain < n_chain - 1) { ok = fold_G(w, cur_chain > 0); cur_chain++; }
+            prev_folded = n_chain > 1;
             base += (uint32_t)nst;
             if (WANT_LOG) log_acc_total += (double)log_acc;
         }
@@ -1129,7 +1177,7 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
         if (!first_item && ok) {
             ok = mbar_wait(BAR_GFULL, g_phase, abort_flag, 9);
             tc_fence_after();
-            drain_G(prev_w);
+            drain_G(prev_w, prev_folded);
         }
         if (WANT_LOG) {
             double v = warp_sum(log_acc_total);
@@ -1217,6 +1265,7 @@ static void tp_base_args(nbmf_handle *h, TPState *s, int owner_rows, bool want_l
     stream_steps = (S_rows + 63) / 64;
     a.dexp = s->dexp; a.dacc = s->dacc; a.derr = s->derr; a.item_ctr = s->item_ctr;
     a.want_log = want_log;
+    a.sub_steps = s->sub_steps;
     // the precision variant was fixed for the session by nbmf_resolve_path (tp_auto_mode under AUTO)
     a.use_lo = (h->path_mode == NBMF_PATH_TENSOR || h->path_mode == NBMF_PATH_TENSOR_LO8) ? 1 : 0;
     a.use_lo8 = (h->path_mode == NBMF_PATH_TENSOR_LO8) ? 1 : 0;
