@@ -31,12 +31,15 @@
 #define GIBBS_WMAX 8          // warps per block (rows per tile = 32 x warps; the launch picks 4..8 to fit F)
 #define GIBBS_CT_MAX 8        // sub-tiles per block (row counts of a block fit 16 bits)
 template <int KT> struct GibbsSmem {
-    static constexpr int NB = GIBBS_NB(KT), KEYS = 2 * KT, ROWS = 32 * GIBBS_WMAX;
+    static constexpr int NB = GIBBS_NB(KT), KEYS = 2 * KT;
     static constexpr size_t H_BYTES = (size_t)2 * NB * KT * 4;          // float  sH[2][NB][KT]
-    static constexpr size_t F_BYTES = (size_t)GIBBS_WMAX * KT * 32 * 2; // ushort hF[warp][KT][32]
-    static constexpr size_t K_BYTES = (size_t)NB * ROWS;                // uchar  sK[NB][ROWS]: key of (column, row), 0xFF = none
-    static constexpr size_t C_BYTES = (size_t)KEYS * ROWS * 4;          // uint   hC[KEYS][thread]
-    static constexpr size_t BYTES = H_BYTES + F_BYTES + K_BYTES + C_BYTES;
+    // per block of `warps` warps (rows = 32 warps): the launch sizes the dynamic shared memory with bytes(warps)
+    static constexpr size_t f_bytes(int warps) { return (size_t)warps * KT * 32 * 2; }        // ushort hF[warp][KT][32]
+    static constexpr size_t k_bytes(int warps) { return (size_t)NB * 32 * warps; }            // uchar  sK[NB][rows]: key of (column, row), 0xFF = none
+    static constexpr int c_stride(int warps) { return 32 * warps + 2; }                        // ushort hC[KEYS][threads + 2]: odd word stride, no bank conflicts across keys
+    static constexpr size_t c_bytes(int warps) { return (size_t)KEYS * c_stride(warps) * 2; }
+    static constexpr size_t bytes(int warps) { return H_BYTES + f_bytes(warps) + k_bytes(warps) + ((c_bytes(warps) + 15) / 16) * 16; }
+    static constexpr size_t BYTES = bytes(GIBBS_WMAX);
 };
 
 // float uniform in (0,1): 23 bits + 1/2, exactly representable, so it is never 0 and never rounds to 1
@@ -229,14 +232,15 @@ __global__ void __launch_bounds__(32 * GIBBS_WMAX) gibbs_sweep_kt_kernel(GibbsSw
 {
     static_assert(KT == 4 || KT == 8 || KT == 16 || KT == 32, "KT");
     constexpr int KEYS = 2 * KT;                          // (label, bit) keys: key = 2 label + bit
-    constexpr int NB = GIBBS_NB(KT), ROWS = 32 * GIBBS_WMAX;
+    constexpr int NB = GIBBS_NB(KT);
     extern __shared__ __align__(16) unsigned char gsm[];
-    float (*sH)[NB][KT] = reinterpret_cast<float (*)[NB][KT]>(gsm);                                  // [bit][column][k] Beta factors
-    unsigned short (*hF)[KT][32] = reinterpret_cast<unsigned short (*)[KT][32]>(gsm + GibbsSmem<KT>::H_BYTES);   // [warp][k][lane] private row histograms
-    unsigned char (*sK)[ROWS] = reinterpret_cast<unsigned char (*)[ROWS]>(gsm + GibbsSmem<KT>::H_BYTES + GibbsSmem<KT>::F_BYTES);
-    uint32_t (*hC)[ROWS] = reinterpret_cast<uint32_t (*)[ROWS]>(gsm + GibbsSmem<KT>::H_BYTES + GibbsSmem<KT>::F_BYTES + GibbsSmem<KT>::K_BYTES);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nwarps = blockDim.x >> 5, nthreads = blockDim.x;
+    const int cstride = GibbsSmem<KT>::c_stride(nwarps);
+    float (*sH)[NB][KT] = reinterpret_cast<float (*)[NB][KT]>(gsm);                                  // [bit][column][k] Beta factors
+    unsigned short (*hF)[KT][32] = reinterpret_cast<unsigned short (*)[KT][32]>(gsm + GibbsSmem<KT>::H_BYTES);   // [warp][k][lane] private row histograms
+    unsigned char *sK = gsm + GibbsSmem<KT>::H_BYTES + GibbsSmem<KT>::f_bytes(nwarps);               // [column][row of the tile]
+    unsigned short *hC = reinterpret_cast<unsigned short *>(sK + GibbsSmem<KT>::k_bytes(nwarps));    // [key][thread], row stride cstride
     const int64_t fw = (int64_t)blockIdx.y * nwarps + warp;   // bit word (32 rows) of this warp
     const int64_t f = fw * 32 + lane;
     const bool row_ok = f < a.F;
@@ -248,7 +252,7 @@ __global__ void __launch_bounds__(32 * GIBBS_WMAX) gibbs_sweep_kt_kernel(GibbsSw
     const bool p2_on = tid < NB * groups;
 #pragma unroll
     for (int k = 0; k < KT; k++) hF[warp][k][lane] = 0;
-    for (int i = tid; i < KEYS * ROWS; i += nthreads) (&hC[0][0])[i] = 0;
+    for (int i = tid; i < KEYS * cstride; i += nthreads) hC[i] = 0;
     float w[KT];
 #pragma unroll
     for (int k4 = 0; k4 < KT; k4 += 4) {
@@ -314,20 +318,20 @@ __global__ void __launch_bounds__(32 * GIBBS_WMAX) gibbs_sweep_kt_kernel(GibbsSw
                     if (obs) { hF[warp][kz][lane] += 1; key = 2 * kz + v; }
                     if (a.Zout && row_ok) a.Zout[f + a.F * n] = obs ? kz : NBMF_NA_INTEGER;
                 }
-                sK[j][tid] = (unsigned char)key;
+                sK[j * nthreads + tid] = (unsigned char)key;
             }
         }
         __syncthreads();
         // ---- phase 2: thread = (column, row group): the column's keys into the thread's private histogram column
         if (p2_on && p2col < nb) {
-            const uint32_t *kw = reinterpret_cast<const uint32_t *>(&sK[p2col][0]);
+            const uint32_t *kw = reinterpret_cast<const uint32_t *>(sK + p2col * nthreads);
             const int w0 = p2grp * gwords, w1 = min(8 * nwarps, w0 + gwords);
             for (int q = w0; q < w1; q++) {
                 const uint32_t kk = kw[q];
 #pragma unroll
                 for (int b = 0; b < 4; b++) {
                     const uint32_t key = (kk >> (8 * b)) & 0xFFu;
-                    if (key != 0xFFu) hC[key][tid] += 1;
+                    if (key != 0xFFu) hC[key * cstride + tid] += 1;
                 }
             }
         }
@@ -336,7 +340,7 @@ __global__ void __launch_bounds__(32 * GIBBS_WMAX) gibbs_sweep_kt_kernel(GibbsSw
         for (int i = tid; i < nb * KEYS; i += nthreads) {
             const int j = i % nb, kk = i / nb;            // consecutive threads: consecutive columns (bank = column)
             int cnt = 0;
-            for (int g = 0; g < groups; g++) { cnt += (int)hC[kk][g * NB + j]; hC[kk][g * NB + j] = 0; }
+            for (int g = 0; g < groups; g++) { cnt += (int)hC[kk * cstride + g * NB + j]; hC[kk * cstride + g * NB + j] = 0; }
             const int64_t idx = (2 * (n0 + j) + (kk & 1)) * KT + (kk >> 1);
             if (a.cn_atomic) { if (cnt) atomicAdd(a.cNp + idx, cnt); }
             else a.cNp[(int64_t)blockIdx.y * 2 * a.N * KT + idx] = cnt;

@@ -1235,7 +1235,7 @@ static cudaError_t launch_gibbs_sweep(const GibbsSweepArgs &a, dim3 grid, int wa
 {
     cudaError_t e = cudaFuncSetAttribute(gibbs_sweep_kt_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GibbsSmem<KT>::BYTES);
     if (e != cudaSuccess) return e;
-    gibbs_sweep_kt_kernel<KT><<<grid, 32 * warps, GibbsSmem<KT>::BYTES, st>>>(a);
+    gibbs_sweep_kt_kernel<KT><<<grid, 32 * warps, GibbsSmem<KT>::bytes(warps), st>>>(a);
     return cudaGetLastError();
 }
 

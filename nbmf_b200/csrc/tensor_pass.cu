@@ -998,12 +998,11 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
                 tc_wait_ld();
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
-                    float4 v = make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
-                    if (fold) {
-                        const float4 o = *reinterpret_cast<const float4 *>(dst + i);
-                        v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
-                    }
-                    *reinterpret_cast<float4 *>(dst + i) = v;
+                    if (fold)   // no read latency in the stalled section; same thread, same address: coherence order = program order
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i), "f"(__uint_as_float(r[i])), "f"(__uint_as_float(r[i + 1])),
+                                     "f"(__uint_as_float(r[i + 2])), "f"(__uint_as_float(r[i + 3])) : "memory");
+                    else
+                        *reinterpret_cast<uint4 *>(dst + i) = make_uint4(r[i], r[i + 1], r[i + 2], r[i + 3]);
                 }
             }
         };
@@ -1079,8 +1078,6 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
             int cur_chain = 0;
             PROF_ACC(0);
             for (int t = tfirst; t < nst && ok; t += 4) {
-                while (ok && t >= (cur_chain + 1) * sub) { ok = fold_G(w, cur_chain > 0); cur_chain++; }   // this group's steps of the chain are done
-                if (!ok) break;
                 uint32_t sel[WPS], vv[WPS];
 #pragma unroll
                 for (int i = 0; i < WPS; i++) {
@@ -1166,6 +1163,9 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
                 mbar_arrive(bar_rready);
                 r_par ^= 1u;
                 PROF_ACC(6);
+                // This was the group's first step of a new chain: its R is on its way, so stage 2 can resume the moment the
+                // old chain has been folded -- which this group does now (every group does, after its own first step).
+                while (ok && t >= (cur_chain + 1) * sub) { ok = fold_G(w, cur_chain > 0); cur_chain++; }
             }
             // chains this group has no step beyond (short tail): every group takes part in every fold
             while (ok && cur_chain < n_chain - 1) { ok = fold_G(w, cur_chain > 0); cur_chain++; }

@@ -2,7 +2,7 @@
 tensor-pipe / FP32-pipe utilisation and achieved HBM GB/s"): per-iteration time of VB_aspect on the FP64 tensor pipe
 (DMMA, the AUTO choice for K <= 32), the FP32 FFMA kernel, the FP64 SIMT kernel (Kp > 128 only in production; forced
 here with NBMF_FP64_KERNEL=simt in a child process) and -- where K allows -- the tcgen05 path.
-    python tools/smallk_bench.py [quick]"""
+    python tools/smallk_bench.py [quick] [shapes=i,j,...] [iters=n]      (shape indices into SHAPES; for ncu captures)"""
 import json
 import os
 import subprocess
@@ -36,8 +36,11 @@ def main():
     from nbmf_b200 import _lib
     simt = os.environ.get("NBMF_FP64_KERNEL") == "simt"
     out = []
-    for F, N, K, tag in SHAPES:
-        iters = 20 if F * N * K < 1e10 else 5
+    pick = [a.split("=")[1] for a in sys.argv if a.startswith("shapes=")]
+    shapes = [SHAPES[int(i)] for i in pick[0].split(",")] if pick else SHAPES
+    fixed = [int(a.split("=")[1]) for a in sys.argv if a.startswith("iters=")]
+    for F, N, K, tag in shapes:
+        iters = fixed[0] if fixed else (20 if F * N * K < 1e10 else 5)
         modes = [("fp64 simt", _lib.PREC_FP64)] if simt else [("fp64 dmma", _lib.PREC_FP64), ("fp32 ffma", _lib.PREC_FP32)]
         if not simt and K > 32:
             modes.append(("tcgen05 hi+lo8", _lib.PREC_TENSOR_LO8))
