@@ -249,3 +249,31 @@ def test_vb_aspect_bits_handle_reuse_across_K():
         assert (path == _lib.PATH_FP64) == (K <= 32), (K, path)
         assert relF(W1, W0) < 1e-5 and relF(H1, H0) < 1e-5 and abs(lb1[-1] - lb0[-1]) < 1e-5 * abs(lb0[-1])
     e1.close()
+
+
+@pytest.mark.parametrize("ndev", [1, 2])
+def test_group_vb_aspect_bits_equals_single_handle(ndev):
+    """The one-call host-memory form over a device group: every device uploads its own column block of the bit plane
+    (pipelined with its first iteration), n_total goes up once (device 0) and reaches the others over NVLink, E_W comes
+    back from device 0 only."""
+    from nbmf_b200 import Engine, _lib
+    from nbmf_b200.api import Group
+    from tests.test_gpu_pipeline import _pack_cols
+    if _ngpu() < ndev:
+        pytest.skip(f"needs {ndev} GPUs")
+    F, N, K, it = 512, 2048, 64, 3
+    V, _, _ = oracle.generate(F, N, 4, 0.8, 0.8, 11)
+    V = np.asfortranarray(V)
+    Z = oracle.random_labels(V, K, 12)
+    bits = _pack_cols(V)
+    e0 = Engine(precision=_lib.PREC_TENSOR_LO8)
+    e0.set_data(V); e0.init_from_labels(Z, K)
+    stats = e0.get_stats(K)
+    W0, H0, lb0 = e0.vb_aspect_bits(bits, F, N, K, stats, 1.0, 1.0, 0.5, iter=it, checklb=True)
+    e0.close()
+    g = Group(_devices(ndev), precision=_lib.PREC_TENSOR_LO8, pipe_block_cols=256)
+    W1, H1, lb1 = g.vb_aspect_bits(bits, F, N, K, stats, 1.0, 1.0, 0.5, iter=it, checklb=True)
+    g.close()
+    assert relF(W1, W0) < 2e-6 and relF(H1, H0) < 2e-6 and np.allclose(lb1, lb0, rtol=1e-6)
+    o = oracle.vb_aspect(V, Z, K, 1.0, 1.0, 0.5, iter=it, checklb=True)
+    assert relF(W1, o["E_W"]) < 1e-5 and relF(H1, o["E_H"]) < 1e-5 and abs(lb1[-1] - o["lowerbounds"][-1]) < 1e-5 * abs(o["lowerbounds"][-1])
