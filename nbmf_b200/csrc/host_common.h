@@ -36,6 +36,7 @@ int nbmf_max_ranks_u64(nbmf_handle *h, unsigned long long *buf, size_t count, cu
 int nbmf_bcast_root(nbmf_handle *h, void *buf, size_t bytes, cudaStream_t st);
 // every rank owns rows [r * ceil(rows/G), ...) of `buf` (rows of row_bytes bytes): make the array whole on all ranks
 int nbmf_allgather_rows(nbmf_handle *h, void *buf, size_t row_bytes, int64_t rows_total, cudaStream_t st);
+int nbmf_allgather_rows_multi(nbmf_handle *h, void *const *bufs, const size_t *row_bytes, int n_bufs, int64_t rows_total, cudaStream_t st);
 // the row block of rank `rank` under that partition
 static inline void nbmf_row_block(int64_t rows_total, int world, int rank, int64_t *lo, int64_t *hi)
 {

@@ -149,21 +149,39 @@ int nbmf_bcast_root(nbmf_handle *h, void *buf, size_t bytes, cudaStream_t st)
     return NBMF_OK;
 }
 
-int nbmf_allgather_rows(nbmf_handle *h, void *buf, size_t row_bytes, int64_t rows_total, cudaStream_t st)
+// several arrays with the same row partition in ONE grouped NCCL launch (bufs[i] has rows of row_bytes[i] bytes)
+int nbmf_allgather_rows_multi(nbmf_handle *h, void *const *bufs, const size_t *row_bytes, int n_bufs, int64_t rows_total, cudaStream_t st)
 {
     if (!h->comm || h->comm_world <= 1) return NBMF_OK;
-    // blocks of unequal length (the last ranks may own fewer rows): one broadcast per owner, grouped
+    const int G = h->comm_world;
+    const int64_t per = (rows_total + G - 1) / G;
+    const bool even = per * G == rows_total;             // equal blocks: one all-gather per array; else one broadcast per owner
     NCCLCK(h, ncclGroupStart());
-    for (int r = 0; r < h->comm_world; r++) {
-        int64_t lo, hi;
-        nbmf_row_block(rows_total, h->comm_world, r, &lo, &hi);
-        if (hi <= lo) continue;
-        char *p = (char *)buf + (size_t)lo * row_bytes;
-        ncclResult_t e = ncclBroadcast(p, p, (size_t)(hi - lo) * row_bytes, ncclChar, r, (ncclComm_t)h->comm, st);
-        if (e != ncclSuccess) { ncclGroupEnd(); h->err = std::string("ncclBroadcast: ") + ncclGetErrorString(e); return NBMF_ERR_CUDA; }
+    for (int i = 0; i < n_bufs; i++) {
+        char *base = (char *)bufs[i];
+        if (even) {
+            ncclResult_t e = ncclAllGather(base + (size_t)h->comm_rank * per * row_bytes[i], base, (size_t)per * row_bytes[i], ncclChar,
+                                           (ncclComm_t)h->comm, st);
+            if (e != ncclSuccess) { ncclGroupEnd(); h->err = std::string("ncclAllGather: ") + ncclGetErrorString(e); return NBMF_ERR_CUDA; }
+            continue;
+        }
+        for (int r = 0; r < G; r++) {
+            int64_t lo, hi;
+            nbmf_row_block(rows_total, G, r, &lo, &hi);
+            if (hi <= lo) continue;
+            char *p = base + (size_t)lo * row_bytes[i];
+            ncclResult_t e = ncclBroadcast(p, p, (size_t)(hi - lo) * row_bytes[i], ncclChar, r, (ncclComm_t)h->comm, st);
+            if (e != ncclSuccess) { ncclGroupEnd(); h->err = std::string("ncclBroadcast: ") + ncclGetErrorString(e); return NBMF_ERR_CUDA; }
+        }
     }
     NCCLCK(h, ncclGroupEnd());
     return NBMF_OK;
+}
+
+int nbmf_allgather_rows(nbmf_handle *h, void *buf, size_t row_bytes, int64_t rows_total, cudaStream_t st)
+{
+    void *bufs[1] = {buf};
+    return nbmf_allgather_rows_multi(h, bufs, &row_bytes, 1, rows_total, st);
 }
 
 // ---------------------------------------------------------------------------

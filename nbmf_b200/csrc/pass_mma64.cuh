@@ -138,6 +138,7 @@ __global__ void __launch_bounds__(256) pass_mma64_kernel(Mma64Args a)
         }
         // ---- R = sel / S in the accumulator layout: element e of tile (i, j) is
         //      lane w1l + 8 i + g, streamed row w1c + 8 j + 2 t + e
+        double dprod = 1.0;   // product of the step's selected D (16 per thread, each >= ~1e-9): one logarithm per step
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             const int li = w1l + i * 8 + g;
@@ -156,11 +157,13 @@ __global__ void __launch_bounds__(256) pass_mma64_kernel(Mma64Args a)
                     act = act && (r0 + c + e < r_end) && (l0 + li < a.L);
                     const double d = s[i][j][e];
                     r[e] = act ? 1.0 / d : 0.0;
-                    if (WANT_LOG && act) ell += log(d);
+                    if (WANT_LOG) dprod *= act ? d : 1.0;
                 }
                 *reinterpret_cast<double2 *>(Rs + li * C::LDR + c) = make_double2(r[0], r[1]);
             }
+            if (WANT_LOG && dprod < 1e-200) { ell += log(dprod); dprod = 1.0; }   // four factors between checks: no underflow for D > 1e-27
         }
+        if (WANT_LOG) ell += log(dprod);
         __syncthreads();
         // ---- GEMM 2: G += R W
 #pragma unroll 4

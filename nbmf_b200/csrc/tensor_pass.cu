@@ -281,6 +281,8 @@ __global__ void tp_max_kernel(const double *__restrict__ x, int64_t count, unsig
     }
 }
 
+__global__ void tp_set_bits_kernel(unsigned long long *dst, unsigned long long bits) { if (threadIdx.x == 0) dst[0] = bits; }
+
 // exponent e with max * 2^e in [2^14, 2^15)
 __global__ void tp_exp_kernel(const unsigned long long *dmax, int *dexp)
 {
@@ -444,12 +446,13 @@ int tp_convert_operands(nbmf_handle *h, bool rows_sliced)
     const int64_t r0 = rows_sliced ? h->row_lo : 0, r1 = rows_sliced ? h->row_hi : h->F;
     const int64_t ca = (r1 - r0) * (int64_t)KP, cb = 2 * h->N * (int64_t)KP, oa = r0 * (int64_t)KP;
     cudaMemsetAsync(s->dmax, 0, 16, h->stream);
-    if (ca > 0) tp_max_kernel<<<(unsigned)std::min<int64_t>(1024, (ca + 255) / 256), 256, 0, h->stream>>>(h->A + oa, ca, s->dmax);
+    // The scale of A has to be the same on every rank.  Every element of A is a probability-like quantity in (0, 1]
+    // (exp(E log W) or E_W), so a row-sliced session -- every iteration of it, the first included -- uses the fixed
+    // exponent 15 (max * 2^15 <= 32768 fits f16) instead of a max over all rows, which would be a collective on the
+    // critical path; only the headroom for elements below 2^-29 of the largest changes.
+    if (h->vb_sliced) tp_set_bits_kernel<<<1, 32, 0, h->stream>>>(s->dmax, 0x3FE8000000000000ull /* 0.75 -> exponent 15 */);
+    else if (ca > 0) tp_max_kernel<<<(unsigned)std::min<int64_t>(1024, (ca + 255) / 256), 256, 0, h->stream>>>(h->A + oa, ca, s->dmax);
     tp_max_kernel<<<(unsigned)std::min<int64_t>(1024, (cb + 255) / 256), 256, 0, h->stream>>>(h->BB, cb, s->dmax + 1);
-    if (rows_sliced) {   // the scale of A is the maximum over ALL rows (positive doubles order like their bit patterns)
-        int rc = nbmf_max_ranks_u64(h, s->dmax, 1, h->stream);
-        if (rc) return rc;
-    }
     tp_exp_kernel<<<1, 32, 0, h->stream>>>(s->dmax, s->dexp);
     if (ca > 0) tp_split_kernel<<<(unsigned)((ca + 255) / 256), 256, 0, h->stream>>>(h->A + oa, ca, s->dexp, 0, s->A_hi + oa, s->A_lo + oa, s->A_lo8 + oa);
     tp_split_kernel<<<(unsigned)((cb + 255) / 256), 256, 0, h->stream>>>(h->BB, cb, s->dexp, 1, s->B_hi, s->B_lo, s->B_lo8);
@@ -459,10 +462,10 @@ int tp_convert_operands(nbmf_handle *h, bool rows_sliced)
     if (rows_sliced) {
         // the f16 operands of the other ranks' rows: hi always (both passes), lo for the ELBO correction and the
         // hi+lo variant, the e5m2 copy for the LO8 variant -- 2 + 2 (+ 1) bytes per element instead of the 8 of A
-        int rc;
-        if ((rc = nbmf_allgather_rows(h, s->A_hi, (size_t)KP * 2, h->F, h->stream))) return rc;
-        if ((rc = nbmf_allgather_rows(h, s->A_lo, (size_t)KP * 2, h->F, h->stream))) return rc;
-        if (h->path_mode == NBMF_PATH_TENSOR_LO8 && (rc = nbmf_allgather_rows(h, s->A_lo8, (size_t)KP, h->F, h->stream))) return rc;
+        void *bufs[3] = {s->A_hi, s->A_lo, s->A_lo8};
+        const size_t rb[3] = {(size_t)KP * 2, (size_t)KP * 2, (size_t)KP};
+        int rc = nbmf_allgather_rows_multi(h, bufs, rb, h->path_mode == NBMF_PATH_TENSOR_LO8 ? 3 : 2, h->F, h->stream);   // one NCCL launch
+        if (rc) return rc;
     }
     return NBMF_OK;
 }
