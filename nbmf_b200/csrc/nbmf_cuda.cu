@@ -793,6 +793,7 @@ extern "C" int nbmf_vb_step(nbmf_handle *h, int checklb)
         if ((rc = exchange(h, h->GF, (size_t)h->F * h->Kp))) return rc;
         CK(cudaEventRecord(h->ev[4], h->stream));
         if (checklb && (rc = tp_log_correction(h, 0, h->scal + SC_SUMLOGD))) return rc;
+        if (checklb && (rc = tp_log_correction_rows_slice(h, h->scal + SC_SUMLOGD))) return rc;
     } else {
     // Dirichlet-side statistic: owner = rows, reduce over the local columns, then
     // the one exchange step, then n_total = A (.) G_F
@@ -809,6 +810,7 @@ extern "C" int nbmf_vb_step(nbmf_handle *h, int checklb)
     if ((rc = run_pass(h, 0, nullptr))) return rc;
     if (checklb && use_tensor_path(h) && (rc = tp_log_correction(h, 0, h->scal + SC_SUMLOGD))) return rc;
     if ((rc = exchange_end(h))) return rc;
+    if (checklb && use_tensor_path(h) && (rc = tp_log_correction_rows_slice(h, h->scal + SC_SUMLOGD))) return rc;
     }
     if (use_tensor_path(h)) {
         if ((rc = tp_finalize(h))) return rc;

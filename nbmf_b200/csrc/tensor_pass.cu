@@ -376,37 +376,32 @@ __global__ void tp_logcorr_kernel(const double *__restrict__ U, const __half *__
     if (threadIdx.x == 0) atomicAdd(sumlogD, t);
 }
 
-// the same with U - U_hi taken from the f16 lo part (exact to 2^-22 of U): a row-sliced session holds the fp64 A of
-// its own rows only, the f16 parts of all of them
-__global__ void tp_logcorr_lo_kernel(const __half *__restrict__ Ulo, const double *__restrict__ G, int64_t count, const int *dexp,
-                                     int which, double *sumlogD)
-{
-    __shared__ double sh[32];
-    const double inv = ldexp(1.0, -dexp[which]);
-    double t = 0.0;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
-        t += (double)__half2float(Ulo[i]) * inv * G[i];
-    t = block_sum(t, sh);
-    if (threadIdx.x == 0) atomicAdd(sumlogD, t);
-}
-
 int tp_log_correction(nbmf_handle *h, int owner_rows, double *sumlogD)
 {
     TPState *s = (TPState *)h->tp;
     if (!s || !sumlogD) return NBMF_OK;
     const int64_t cnt = (owner_rows ? h->F : 2 * h->N) * (int64_t)s->KP;
-    if (owner_rows && h->vb_sliced) {
-        tp_logcorr_lo_kernel<<<(unsigned)std::min<int64_t>(2048, (cnt + 255) / 256), 256, 0, h->stream>>>(s->A_lo, h->GF, cnt, s->dexp, 0, sumlogD);
-        cudaError_t e0 = cudaGetLastError();
-        if (e0 != cudaSuccess) { h->err = std::string("tp_log_correction: ") + cudaGetErrorString(e0); return NBMF_ERR_CUDA; }
-        h->timing.launches += 1;
-        return NBMF_OK;
-    }
+    // Row-sliced session: the correction is linear in G, so it is taken AFTER the exchange, by every rank over its own
+    // rows against the summed G_F (tp_log_correction_rows_slice) -- the ranks' shares add up to the same total, no rank
+    // needs the other rows' fp64 A or their lo parts, and the work is 1/G of it.
+    if (owner_rows && h->vb_sliced) return NBMF_OK;
     tp_logcorr_kernel<<<(unsigned)std::min<int64_t>(2048, (cnt + 255) / 256), 256, 0, h->stream>>>(
         owner_rows ? h->A : h->BB, owner_rows ? s->A_hi : s->B_hi,
         owner_rows ? h->GF : h->GN, cnt, s->dexp, owner_rows ? 0 : 1, sumlogD);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { h->err = std::string("tp_log_correction: ") + cudaGetErrorString(e); return NBMF_ERR_CUDA; }
+    h->timing.launches += 1;
+    return NBMF_OK;
+}
+
+int tp_log_correction_rows_slice(nbmf_handle *h, double *sumlogD)
+{
+    TPState *s = (TPState *)h->tp;
+    if (!s || !sumlogD || !h->vb_sliced || h->row_hi <= h->row_lo) return NBMF_OK;
+    const int64_t o = h->row_lo * (int64_t)s->KP, cnt = (h->row_hi - h->row_lo) * (int64_t)s->KP;
+    tp_logcorr_kernel<<<(unsigned)std::min<int64_t>(2048, (cnt + 255) / 256), 256, 0, h->stream>>>(h->A + o, s->A_hi + o, h->GF + o, cnt, s->dexp, 0, sumlogD);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { h->err = std::string("tp_log_correction_rows_slice: ") + cudaGetErrorString(e); return NBMF_ERR_CUDA; }
     h->timing.launches += 1;
     return NBMF_OK;
 }
@@ -460,11 +455,11 @@ int tp_convert_operands(nbmf_handle *h, bool rows_sliced)
     if (e != cudaSuccess) { h->err = std::string("tp_convert_operands: ") + cudaGetErrorString(e); return NBMF_ERR_CUDA; }
     h->timing.launches += 5;
     if (rows_sliced) {
-        // the f16 operands of the other ranks' rows: hi always (both passes), lo for the ELBO correction and the
-        // hi+lo variant, the e5m2 copy for the LO8 variant -- 2 + 2 (+ 1) bytes per element instead of the 8 of A
-        void *bufs[3] = {s->A_hi, s->A_lo, s->A_lo8};
-        const size_t rb[3] = {(size_t)KP * 2, (size_t)KP * 2, (size_t)KP};
-        int rc = nbmf_allgather_rows_multi(h, bufs, rb, h->path_mode == NBMF_PATH_TENSOR_LO8 ? 3 : 2, h->F, h->stream);   // one NCCL launch
+        // the f16 operands of the other ranks' rows -- 2 (+ 2 or + 1) bytes per element instead of the 8 of A
+        // what the passes read of the other ranks' rows: hi always; the lo part in the form the variant streams it
+        void *bufs[2] = {s->A_hi, h->path_mode == NBMF_PATH_TENSOR_LO8 ? (void *)s->A_lo8 : (void *)s->A_lo};
+        const size_t rb[2] = {(size_t)KP * 2, h->path_mode == NBMF_PATH_TENSOR_LO8 ? (size_t)KP : (size_t)KP * 2};
+        int rc = nbmf_allgather_rows_multi(h, bufs, rb, h->path_mode == NBMF_PATH_TENSOR_FAST ? 1 : 2, h->F, h->stream);   // one NCCL launch
         if (rc) return rc;
     }
     return NBMF_OK;

@@ -10,6 +10,7 @@ int tp_auto_mode(const nbmf_handle *h, int K, int horizon);
 int tp_prepare(nbmf_handle *h);               // allocate f16 operand buffers + tensor maps
 int tp_convert_operands(nbmf_handle *h, bool rows_sliced = false);   // rows_sliced: own rows of A only, then all-gather of the f16 parts      // A, BB (fp64) -> scaled f16 hi/lo
 int tp_pass(nbmf_handle *h, int owner_rows, double *sumlogD);
+int tp_log_correction_rows_slice(nbmf_handle *h, double *sumlogD);   // row-sliced sessions: after the exchange, own rows
 // both passes, column block by column block behind the events of a pipelined upload
 int tp_passes_pipelined(nbmf_handle *h, int n_blocks, const int64_t *n0, cudaEvent_t *ev,
                         int (*prepare_block)(nbmf_handle *, int64_t, int64_t), double *sumlogD);
