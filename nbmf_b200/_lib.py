@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "libnbmf_cuda.so")
+# NBMF_LIB_VARIANT=prof selects the instrumented build (libnbmf_cuda_prof.so, `make prof`): debug aid of tools/role_profile.py
+SO_PATH = os.path.join(HERE, "libnbmf_cuda" + ("_" + os.environ["NBMF_LIB_VARIANT"] if os.environ.get("NBMF_LIB_VARIANT") else "") + ".so")
 
 NBMF_OK = 0
 PREC_AUTO, PREC_FP64, PREC_TENSOR, PREC_TENSOR_FAST, PREC_TENSOR_LO8, PREC_FP32 = 0, 1, 2, 3, 4, 5

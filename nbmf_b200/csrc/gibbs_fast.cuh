@@ -11,10 +11,14 @@
 //                        form) and the tile's counts
 //
 // Sweep kernel, per warp = one 32-row bit word of the tile, all NB columns:
-//   * the row's K weights stay in registers; the column's K Beta factors come from shared memory as
-//     four broadcast 128-bit loads of the table selected by the entry's bit (H and 1-H are both kept)
+//   * a thread samples TWO columns (j, j+1) of its row at a time in packed fp32 (FFMA2: one issue slot per two
+//     multiply-adds).  The row's K weights stay in registers as (w_k, w_k); the Beta factors of the column pair
+//     come from shared memory as (h_j, h_j+1) pairs, K/2 broadcast 128-bit loads from the table selected by the
+//     entries' two bits (four tables per pair: H or 1-H for either column; their strides are offset by 16 bytes,
+//     so the up to four addresses of a warp lie in different banks)
 //   * one Philox4x32-10 block serves four consecutive columns (keyed seed; f, n/4, sweep)
-//   * single pass: the K running sums c_k are kept in registers, the draw is #{k : c_k <= u c_K}
+//   * single pass: the K running sums c_k are kept in registers, the draw is #{k : c_k <= u c_K}, counted as the
+//     sum of K-1 compare results (FSET.BF, added in fp32 pairs)
 //   * row-side counts: the lane owns its row, so its histogram is a private shared-memory column (no
 //     shared-memory atomics) that leaves once per block as one integer atomic per (row, label);
 //   * column-side counts: every entry leaves its (label, bit) key as a byte in a shared-memory tile; after a
@@ -27,12 +31,16 @@
 #pragma once
 #include "common.cuh"
 
-#define GIBBS_NB(KT) ((KT) <= 16 ? 128 : 64)   // columns per sub-tile
+#ifndef GIBBS_NB16
+#define GIBBS_NB16 128       // columns per sub-tile for K <= 16
+#endif
+#define GIBBS_NB(KT) ((KT) <= 16 ? GIBBS_NB16 : 64)   // columns per sub-tile
 #define GIBBS_WMAX 8          // warps per block (rows per tile = 32 x warps; the launch picks 4..8 to fit F)
 #define GIBBS_CT_MAX 8        // sub-tiles per block (row counts of a block fit 16 bits)
 template <int KT> struct GibbsSmem {
     static constexpr int NB = GIBBS_NB(KT), KEYS = 2 * KT;
-    static constexpr size_t H_BYTES = (size_t)2 * NB * KT * 4;          // float  sH[2][NB][KT]
+    static constexpr int COMBO_FLOATS = (NB / 2) * KT * 2 + 4;          // one table of (h_j, h_j+1) pairs, + 16 bytes: the four tables start in different banks
+    static constexpr size_t H_BYTES = (size_t)4 * COMBO_FLOATS * 4;     // float2 sH2[4 = bit_j + 2 bit_j+1][NB/2][KT]
     // per block of `warps` warps (rows = 32 warps): the launch sizes the dynamic shared memory with bytes(warps)
     static constexpr size_t f_bytes(int warps) { return (size_t)warps * KT * 32 * 2; }        // ushort hF[warp][KT][32]
     static constexpr size_t k_bytes(int warps) { return (size_t)NB * 32 * warps; }            // uchar  sK[NB][rows]: key of (column, row), 0xFF = none
@@ -42,6 +50,14 @@ template <int KT> struct GibbsSmem {
     static constexpr size_t bytes(int warps) { return H_BYTES + f_bytes(warps) + k_bytes(warps) + ((c_bytes(warps) + 15) / 16) * 16 + v_bytes(warps); }
     static constexpr size_t BYTES = bytes(GIBBS_WMAX);
 };
+
+// 1.0f if a <= b, else 0.0f (FSET.BF: one instruction; the inverse-CDF count is a sum of these)
+__device__ __forceinline__ float le_one(float a, float b)
+{
+    float d;
+    asm("set.le.f32.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
+    return d;
+}
 
 // float uniform in (0,1): 23 bits + 1/2, exactly representable, so it is never 0 and never rounds to 1
 __device__ __forceinline__ float u24(uint32_t x) { return ((float)(x >> 9) + 0.5f) * (1.0f / 8388608.0f); }
@@ -105,7 +121,7 @@ struct GibbsDrawArgs {
     float *w_cur, *h_cur;       // [F][K], [N][K] means of this sweep's counts (E_V on held-out entries)
 };
 
-// One warp per row f, then one per column n; lane k owns component k (KT <= 32).
+// One warp per row f (lane k owns component k, KT <= 32), then one per 32 / KT columns.
 // W_f ~ Dir(gamma + n_total_f) as normalised Gammas (collapsed_gibbs_z.cpp:590-596), every rank of a
 // sharded run drawing the same row from the shared key (seed; f, k, sweep); H_nk ~ Beta(alpha + ones,
 // beta + zeros) as x / (x + y) (:599-605), keyed by the global column.
@@ -145,31 +161,32 @@ __global__ void __launch_bounds__(256) gibbs_draw_kernel(GibbsDrawArgs a)
             for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
             if (lane < KT) a.W[f * KT + lane] = e / s;
         }
-    } else if (wid < a.F + a.N) {
-        const int64_t n = wid - a.F;
+    } else {
+        // columns: 32 / KT of them per warp, lane = (column, component)
+        const int cpw = 32 / KT, k = lane % KT;
+        const int64_t n = (wid - a.F) * cpw + lane / KT;
+        if (n >= a.N) return;
+        const int64_t i1 = (2 * n + 1) * KT + k, i0 = (2 * n) * KT + k;
         int c1 = 0, c0 = 0;
-        if (lane < KT) {
-            const int64_t i1 = (2 * n + 1) * KT + lane, i0 = (2 * n) * KT + lane;
-            if (a.n_parts > 0) {
-                for (int p = 0; p < a.n_parts; p++) {
-                    c1 += a.cNp[(int64_t)p * 2 * a.N * KT + i1];
-                    c0 += a.cNp[(int64_t)p * 2 * a.N * KT + i0];
-                }
-            } else {
-                c1 = a.cN[i1]; c0 = a.cN[i0];
-                if (a.zero_cn) { a.cN[i1] = 0; a.cN[i0] = 0; }
+        if (a.n_parts > 0) {
+            for (int p = 0; p < a.n_parts; p++) {
+                c1 += a.cNp[(int64_t)p * 2 * a.N * KT + i1];
+                c0 += a.cNp[(int64_t)p * 2 * a.N * KT + i0];
             }
+        } else {
+            c1 = a.cN[i1]; c0 = a.cN[i0];
+            if (a.zero_cn) { a.cN[i1] = 0; a.cN[i0] = 0; }
         }
-        if (a.accumulate && lane < K) {
+        if (a.accumulate && k < K) {
             const double hm = (a.alpha + c1) / (a.alpha + a.beta + c1 + c0);
-            a.accH[n * K + lane] += hm;
-            a.h_cur[n * K + lane] = (float)hm;
+            a.accH[n * K + k] += hm;
+            a.h_cur[n * K + k] = (float)hm;
         }
-        if (a.draw && lane < KT) {
+        if (a.draw) {
             float hv = 0.5f, cv = 0.5f;
-            if (lane < K) {
+            if (k < K) {
                 const int64_t ng = n + a.n_offset;
-                PhiloxF rs(a.seed, (uint32_t)ng, (uint32_t)lane | 0x80000000u | ((uint32_t)(ng >> 32) << 16), a.sweep);
+                PhiloxF rs(a.seed, (uint32_t)ng, (uint32_t)k | 0x80000000u | ((uint32_t)(ng >> 32) << 16), a.sweep);
                 float lx, ly;
                 const float x = rs.gamma_log((float)(a.alpha + c1), &lx);
                 const float y = rs.gamma_log((float)(a.beta + c0), &ly);
@@ -179,8 +196,8 @@ __global__ void __launch_bounds__(256) gibbs_draw_kernel(GibbsDrawArgs a)
                 hv = fmaxf(1.0f / (1.0f + expf(dl)), 1e-30f);
                 cv = fmaxf(1.0f / (1.0f + expf(-dl)), 1e-30f);
             }
-            a.HH[(a.N + n) * KT + lane] = hv;
-            a.HH[n * KT + lane] = cv;
+            a.HH[(a.N + n) * KT + k] = hv;
+            a.HH[n * KT + k] = cv;
         }
     }
 }
@@ -238,7 +255,8 @@ __global__ void __launch_bounds__(32 * GIBBS_WMAX) gibbs_sweep_kt_kernel(GibbsSw
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nwarps = blockDim.x >> 5, nthreads = blockDim.x;
     const int cstride = GibbsSmem<KT>::c_stride(nwarps);
-    float (*sH)[NB][KT] = reinterpret_cast<float (*)[NB][KT]>(gsm);                                  // [bit][column][k] Beta factors
+    float *sH2 = reinterpret_cast<float *>(gsm);                                                      // [bit_j + 2 bit_j+1][column pair][k] (h_j, h_j+1)
+    constexpr int CSF = GibbsSmem<KT>::COMBO_FLOATS;
     unsigned short (*hF)[KT][32] = reinterpret_cast<unsigned short (*)[KT][32]>(gsm + GibbsSmem<KT>::H_BYTES);   // [warp][k][lane] private row histograms
     unsigned char *sK = gsm + GibbsSmem<KT>::H_BYTES + GibbsSmem<KT>::f_bytes(nwarps);               // [column][row of the tile]
     unsigned short *hC = reinterpret_cast<unsigned short *>(sK + GibbsSmem<KT>::k_bytes(nwarps));    // [key][thread], row stride cstride
@@ -256,81 +274,93 @@ __global__ void __launch_bounds__(32 * GIBBS_WMAX) gibbs_sweep_kt_kernel(GibbsSw
 #pragma unroll
     for (int k = 0; k < KT; k++) hF[warp][k][lane] = 0;
     for (int i = tid; i < KEYS * cstride; i += nthreads) hC[i] = 0;
-    float w[KT];
+    float2 ww[KT];                                        // (w_k, w_k)
 #pragma unroll
     for (int k4 = 0; k4 < KT; k4 += 4) {
         const float4 v = row_ok ? __ldg(reinterpret_cast<const float4 *>(a.W + f * KT + k4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        w[k4] = v.x; w[k4 + 1] = v.y; w[k4 + 2] = v.z; w[k4 + 3] = v.w;
+        ww[k4] = make_float2(v.x, v.x); ww[k4 + 1] = make_float2(v.y, v.y); ww[k4 + 2] = make_float2(v.z, v.z); ww[k4 + 3] = make_float2(v.w, v.w);
     }
+    const int mis = (int)(a.n_offset & 3);                // sub-tiles start at multiples of NB: only a misaligned shard start shifts the Philox blocks
+    const uint32_t pk1 = (uint32_t)(a.seed >> 32) ^ 0x2545F491u;
     for (int st = 0; st < a.ct; st++) {
         const int64_t n0 = ((int64_t)blockIdx.x * a.ct + st) * NB;
         if (n0 >= a.N) break;                             // block-uniform
         const int nb = (int)min((int64_t)NB, a.N - n0);
         __syncthreads();                                  // the previous sub-tile's tables, keys and counts are consumed
-        for (int i = tid; i < 2 * NB * KT; i += nthreads) {
-            const int tb = i / (NB * KT), r = (i / KT) % NB, k = i % KT;
-            sH[tb][r][k] = (r < nb) ? a.HH[((int64_t)tb * a.N + n0 + r) * KT + k] : 0.f;
+        for (int i = tid; i < 4 * (NB / 2) * KT; i += nthreads) {
+            const int combo = i / ((NB / 2) * KT), r = i % ((NB / 2) * KT), j = 2 * (r / KT), k = r % KT;
+            float2 hv;
+            hv.x = (j < nb) ? __ldg(a.HH + ((int64_t)(combo & 1) * a.N + n0 + j) * KT + k) : 0.f;
+            hv.y = (j + 1 < nb) ? __ldg(a.HH + ((int64_t)(combo >> 1) * a.N + n0 + j + 1) * KT + k) : 0.f;
+            *reinterpret_cast<float2 *>(sH2 + combo * CSF + 2 * r) = hv;
         }
         // the sub-tile's bit words, fetched once by the block (a load per column right before its use stalled every warp
-        // for an L2 round trip: 28 % of the stall samples of the first version)
-        for (int i = tid; i < nb * nwarps; i += nthreads) {
+        // for an L2 round trip: 28 % of the stall samples of the first version); columns beyond the matrix: no bits
+        for (int i = tid; i < NB * nwarps; i += nthreads) {
             const int j = i / nwarps, wq = i % nwarps;
             const int64_t wrd = (int64_t)blockIdx.y * nwarps + wq;
-            const bool in = wrd < a.Fw;
+            const bool in = wrd < a.Fw && j < nb;
             sV[i] = in ? __ldg(a.vc + (n0 + j) * a.Fw + wrd) : 0u;
-            sM[i] = a.mc ? (in ? __ldg(a.mc + (n0 + j) * a.Fw + wrd) : 0u) : 0xffffffffu;
+            sM[i] = in ? (a.mc ? __ldg(a.mc + (n0 + j) * a.Fw + wrd) : 0xffffffffu) : 0u;
         }
         __syncthreads();
-        // ---- phase 1: thread = row, loop over the sub-tile's columns
+        // ---- phase 1: thread = row, loop over the sub-tile's columns, two at a time
         for (int j0 = 0; j0 < nb; j0 += 4) {
             // one Philox block per four consecutive GLOBAL columns (keyed by the global column, so the
             // chain does not depend on the sharding); a misaligned shard start straddles two blocks
             const int64_t ng0 = n0 + j0 + a.n_offset;
-            const uint32_t k1 = (uint32_t)(a.seed >> 32) ^ 0x2545F491u;
-            philox4 ra, rb4;
-            const int mis = (int)(ng0 & 3);               // warp-uniform
+            uint32_t rnd[4] = {0u, 0u, 0u, 0u};
             if (word_ok) {
-                ra = philox4x32_10((uint32_t)f, (uint32_t)(ng0 >> 2), (uint32_t)(ng0 >> 34), a.sweep, (uint32_t)a.seed, k1);
-                rb4 = ra;
-                if (mis) rb4 = philox4x32_10((uint32_t)f, (uint32_t)((ng0 >> 2) + 1), (uint32_t)(((ng0 >> 2) + 1) >> 32), a.sweep, (uint32_t)a.seed, k1);
+                const philox4 ra = philox4x32_10((uint32_t)f, (uint32_t)(ng0 >> 2), (uint32_t)(ng0 >> 34), a.sweep, (uint32_t)a.seed, pk1);
+                rnd[0] = ra.x; rnd[1] = ra.y; rnd[2] = ra.z; rnd[3] = ra.w;
+                if (mis) {                                // warp-uniform, sharded runs only
+                    const philox4 rb = philox4x32_10((uint32_t)f, (uint32_t)((ng0 >> 2) + 1), (uint32_t)(((ng0 >> 2) + 1) >> 32), a.sweep, (uint32_t)a.seed, pk1);
+                    const uint32_t all[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+                    for (int jj = 0; jj < 4; jj++) rnd[jj] = mis == 1 ? all[jj + 1] : mis == 2 ? all[jj + 2] : all[jj + 3];
+                }
             }
 #pragma unroll
-            for (int jj = 0; jj < 4; jj++) {
-                const int j = j0 + jj;
+            for (int pp = 0; pp < 2; pp++) {
+                const int j = j0 + 2 * pp;                // columns j and j + 1
                 if (j >= nb) break;                       // block-uniform
-                int key = 0xFF;
+                int key0 = 0xFF, key1 = 0xFF;
                 if (word_ok) {
-                    const int64_t n = n0 + j;
-                    const uint32_t vw = sV[j * nwarps + warp];
-                    const uint32_t mw = sM[j * nwarps + warp];
-                    const bool obs = row_ok && ((mw >> lane) & 1u);
-                    const int v = (vw >> lane) & 1u;
-                    const float4 *hp = reinterpret_cast<const float4 *>(&sH[v][j][0]);
-                    float c[KT];
-                    float run = 0.f;
+                    const uint32_t vw0 = sV[j * nwarps + warp], vw1 = sV[(j + 1) * nwarps + warp];
+                    const uint32_t mw0 = sM[j * nwarps + warp], mw1 = sM[(j + 1) * nwarps + warp];
+                    const bool obs0 = row_ok && ((mw0 >> lane) & 1u), obs1 = row_ok && ((mw1 >> lane) & 1u);
+                    const int v0 = (vw0 >> lane) & 1u, v1 = (vw1 >> lane) & 1u;
+                    const float4 *hp = reinterpret_cast<const float4 *>(sH2 + (v0 + 2 * v1) * CSF + (j >> 1) * (2 * KT));
+                    float2 c[KT];
+                    float2 run = make_float2(0.f, 0.f);
 #pragma unroll
-                    for (int k4 = 0; k4 < KT; k4 += 4) {
-                        const float4 h4 = hp[k4 >> 2];
-                        run = fmaf(w[k4], h4.x, run); c[k4] = run;
-                        run = fmaf(w[k4 + 1], h4.y, run); c[k4 + 1] = run;
-                        run = fmaf(w[k4 + 2], h4.z, run); c[k4 + 2] = run;
-                        run = fmaf(w[k4 + 3], h4.w, run); c[k4 + 3] = run;
+                    for (int k2 = 0; k2 < KT; k2 += 2) {
+                        const float4 h4 = hp[k2 >> 1];    // (h_j[k2], h_j+1[k2], h_j[k2+1], h_j+1[k2+1])
+                        run = __ffma2_rn(ww[k2], make_float2(h4.x, h4.y), run); c[k2] = run;
+                        run = __ffma2_rn(ww[k2 + 1], make_float2(h4.z, h4.w), run); c[k2 + 1] = run;
                     }
-                    const int sel = mis + jj;             // component (sel & 3) of block ra (sel < 4) or rb4
-                    const philox4 &rr = sel < 4 ? ra : rb4;
-                    const uint32_t rb = (sel & 3) == 0 ? rr.x : (sel & 3) == 1 ? rr.y : (sel & 3) == 2 ? rr.z : rr.w;
-                    const float target = u24(rb) * run;
+                    const float2 target = __fmul2_rn(make_float2(u24(rnd[2 * pp]), u24(rnd[2 * pp + 1])), run);
                     // inverse CDF without a second pass: the label is the number of running sums at or
                     // below the target (they are non-decreasing; u < 1 keeps it below the last one, and
                     // a padded component repeats the last sum, so it is never drawn)
-                    int kz = 0;
+                    // counted in fp32 pairs on top of 2^23, where one ulp is 1: the low mantissa bits are the count
+                    float2 n_a = make_float2(8388608.f, 8388608.f), n_b = make_float2(0.f, 0.f);
 #pragma unroll
-                    for (int k = 0; k < KT - 1; k++) kz += (c[k] <= target) ? 1 : 0;
-                    kz = min(kz, a.K - 1);
-                    if (obs) { hF[warp][kz][lane] += 1; key = 2 * kz + v; }
-                    if (a.Zout && row_ok) a.Zout[f + a.F * n] = obs ? kz : NBMF_NA_INTEGER;
+                    for (int k = 0; k < KT - 1; k++) {
+                        const float2 one = make_float2(le_one(c[k].x, target.x), le_one(c[k].y, target.y));
+                        if (k & 1) n_b = __fadd2_rn(n_b, one); else n_a = __fadd2_rn(n_a, one);
+                    }
+                    n_a = __fadd2_rn(n_a, n_b);
+                    const int kz0 = min(__float_as_int(n_a.x) & 0xFF, a.K - 1), kz1 = min(__float_as_int(n_a.y) & 0xFF, a.K - 1);
+                    if (obs0) { hF[warp][kz0][lane] += 1; key0 = 2 * kz0 + v0; }
+                    if (obs1) { hF[warp][kz1][lane] += 1; key1 = 2 * kz1 + v1; }
+                    if (a.Zout && row_ok) {
+                        a.Zout[f + a.F * (n0 + j)] = obs0 ? kz0 : NBMF_NA_INTEGER;
+                        if (j + 1 < nb) a.Zout[f + a.F * (n0 + j + 1)] = obs1 ? kz1 : NBMF_NA_INTEGER;
+                    }
                 }
-                sK[j * nthreads + tid] = (unsigned char)key;
+                sK[j * nthreads + tid] = (unsigned char)key0;
+                sK[(j + 1) * nthreads + tid] = (unsigned char)key1;
             }
         }
         __syncthreads();

@@ -1317,7 +1317,7 @@ static int gibbs_dirber_fast(nbmf_handle *h, int K, double alpha, double beta, d
     int ct = (int)std::max<int64_t>(1, std::min<int64_t>(GIBBS_CT_MAX, (n_tiles * f_tiles) / (6ll * h->sm_count)));
     sw.ct = ct;
     const dim3 sgrid((unsigned)((n_tiles + ct - 1) / ct), (unsigned)f_tiles);
-    const unsigned dgrid = nblk((F + N) * 32, 256);
+    const unsigned dgrid = nblk((F + (N + 32 / KT - 1) / (32 / KT)) * 32, 256);   // a warp per row, a warp per 32 / KT columns
     int kept = 0;
     int rc = NBMF_OK;
     CK(cudaEventRecord(h->ev[0], h->stream));

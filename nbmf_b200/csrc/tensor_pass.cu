@@ -1087,39 +1087,64 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
                 const uint32_t sslot = gs % (uint32_t)C::NS;
                 const uint32_t t_s = tmem + lane_addr + C::COL_S + 64 * sslot;
                 // one half (32 S columns) of the step: select, shared reciprocal, pack to f16
+                // Arithmetic in packed fp32 pairs (FMUL2 / FFMA2: one issue slot per two entries): the epilogue is bound by
+                // issue slots and latency, not by the FMA pipe.  Four entries at a time, A = (a0, a1), B = (b0, b1); entry
+                // a_i shares its reciprocal with b_i: 1/a = b/(ab), 1/b = a/(ab).  An unselected entry takes part as 2^64,
+                // which makes its own R vanish below f16 resolution and leaves its partner's R exact.
                 auto half_step = [&](const int cc, const uint32_t (&s)[32], uint32_t (&rp)[16]) {
+                    const float2 c02 = make_float2(c0, c0), tiny2 = make_float2(ftiny, ftiny);
                     if (ROWS) {
                         // 32 columns = 16 entries (n) x 2 branches, column 2j+b
                         const uint32_t m16 = sel[0] >> (cc * 16);
                         const uint32_t v16 = vv[0] >> (cc * 16);
+                        const float2 c1sq2 = make_float2(c1 * c1, c1 * c1);
 #pragma unroll
-                        for (int i = 0; i < 8; i++) {
-                            // two entries share one reciprocal: 1/s0 = s1/(s0 s1), 1/s1 = s0/(s0 s1);
-                            // a masked entry takes part as 2^64, which makes its own R vanish below
-                            // f16 resolution and leaves its partner's R exact
-                            const int j0 = 2 * i, j1 = 2 * i + 1;
-                            const bool vb0 = (v16 >> j0) & 1u, vb1 = (v16 >> j1) & 1u;
-                            float s0 = __uint_as_float(vb0 ? s[2 * j0 + 1] : s[2 * j0]);
-                            float s1 = __uint_as_float(vb1 ? s[2 * j1 + 1] : s[2 * j1]);
+                        for (int i = 0; i < 4; i++) {
+                            bool vb[4];
+                            float e[4];
+#pragma unroll
+                            for (int m = 0; m < 4; m++) {
+                                const int j = 4 * i + m;
+                                vb[m] = (v16 >> j) & 1u;
+                                e[m] = __uint_as_float(vb[m] ? s[2 * j + 1] : s[2 * j]);
+                            }
                             if (HAS_NA) {
-                                const bool mb0 = (m16 >> j0) & 1u, mb1 = (m16 >> j1) & 1u;
-                                if (WANT_LOG) log_acc += fast_lg2((mb0 ? s0 * c1 : 1.f) * (mb1 ? s1 * c1 : 1.f));
-                                s0 = mb0 ? s0 : fhuge;
-                                s1 = mb1 ? s1 : fhuge;
-                            } else if (WANT_LOG) log_acc += fast_lg2((s0 * c1) * (s1 * c1));
-                            const float tr = c0 * fast_rcp(fmaf(s0, s1, ftiny));
-                            const float r0 = tr * s1, r1 = tr * s0;
-                            rp[j0] = pack_h2_sat(vb0 ? 0.f : r0, vb0 ? r0 : 0.f);
-                            rp[j1] = pack_h2_sat(vb1 ? 0.f : r1, vb1 ? r1 : 0.f);
+                                float lg[4];
+#pragma unroll
+                                for (int m = 0; m < 4; m++) {
+                                    const bool mb = (m16 >> (4 * i + m)) & 1u;
+                                    lg[m] = mb ? e[m] * c1 : 1.f;
+                                    e[m] = mb ? e[m] : fhuge;
+                                }
+                                if (WANT_LOG) log_acc += fast_lg2(lg[0] * lg[2]) + fast_lg2(lg[1] * lg[3]);
+                            }
+                            const float2 A = make_float2(e[0], e[1]), B = make_float2(e[2], e[3]);
+                            const float2 pr = __ffma2_rn(A, B, tiny2);
+                            if (WANT_LOG && !HAS_NA) {
+                                // S * c1 = D: lg2.approx's relative error must apply to log2 D, not to log2 S
+                                const float2 q = __fmul2_rn(pr, c1sq2);
+                                log_acc += fast_lg2(q.x) + fast_lg2(q.y);
+                            }
+                            const float2 t = __fmul2_rn(make_float2(fast_rcp(pr.x), fast_rcp(pr.y)), c02);
+                            const float2 RA = __fmul2_rn(B, t), RB = __fmul2_rn(A, t);
+                            rp[4 * i + 0] = vb[0] ? pack_h2_sat(0.f, RA.x) : pack_h2_sat(RA.x, 0.f);
+                            rp[4 * i + 1] = vb[1] ? pack_h2_sat(0.f, RA.y) : pack_h2_sat(RA.y, 0.f);
+                            rp[4 * i + 2] = vb[2] ? pack_h2_sat(0.f, RB.x) : pack_h2_sat(RB.x, 0.f);
+                            rp[4 * i + 3] = vb[3] ? pack_h2_sat(0.f, RB.y) : pack_h2_sat(RB.y, 0.f);
                         }
                     } else {
                         const uint32_t m32 = sel[cc];
 #pragma unroll
-                        for (int j = 0; j < 16; j++) {
-                            const float a0 = ((m32 >> (2 * j)) & 1u) ? __uint_as_float(s[2 * j]) : fhuge;
-                            const float a1 = ((m32 >> (2 * j + 1)) & 1u) ? __uint_as_float(s[2 * j + 1]) : fhuge;
-                            const float tr = c0 * fast_rcp(fmaf(a0, a1, ftiny));
-                            rp[j] = pack_h2_sat(tr * a1, tr * a0);
+                        for (int i = 0; i < 8; i++) {
+                            float e[4];
+#pragma unroll
+                            for (int m = 0; m < 4; m++) e[m] = ((m32 >> (4 * i + m)) & 1u) ? __uint_as_float(s[4 * i + m]) : fhuge;
+                            const float2 A = make_float2(e[0], e[1]), B = make_float2(e[2], e[3]);
+                            const float2 pr = __ffma2_rn(A, B, tiny2);
+                            const float2 t = __fmul2_rn(make_float2(fast_rcp(pr.x), fast_rcp(pr.y)), c02);
+                            const float2 RA = __fmul2_rn(B, t), RB = __fmul2_rn(A, t);
+                            rp[2 * i] = pack_h2_sat(RA.x, RA.y);
+                            rp[2 * i + 1] = pack_h2_sat(RB.x, RB.y);
                         }
                     }
                 };
@@ -1164,6 +1189,7 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
                 // This was the group's first step of a new chain: its R is on its way, so stage 2 can resume the moment the
                 // old chain has been folded -- which this group does now (every group does, after its own first step).
                 while (ok && t >= (cur_chain + 1) * sub) { ok = fold_G(w, cur_chain > 0); cur_chain++; }
+                PROF_ACC(7);
             }
             // chains this group has no step beyond (short tail): every group takes part in every fold
             while (ok && cur_chain < n_chain - 1) { ok = fold_G(w, cur_chain > 0); cur_chain++; }
