@@ -31,23 +31,22 @@
 #pragma once
 #include "common.cuh"
 
-#ifndef GIBBS_NB16
-#define GIBBS_NB16 128       // columns per sub-tile for K <= 16
+#define GIBBS_NB(KT) 64       // columns per sub-tile
+#ifndef GIBBS_MINB16
+#define GIBBS_MINB16 3        // resident 256-thread blocks the register budget of the K <= 16 kernels is sized for
 #endif
-#define GIBBS_NB(KT) ((KT) <= 16 ? GIBBS_NB16 : 64)   // columns per sub-tile
 #define GIBBS_WMAX 8          // warps per block (rows per tile = 32 x warps; the launch picks 4..8 to fit F)
-#define GIBBS_CT_MAX 8        // sub-tiles per block (row counts of a block fit 16 bits)
+#define GIBBS_CT_MAX 16       // sub-tiles per block (row counts of a block fit 16 bits)
 template <int KT> struct GibbsSmem {
     static constexpr int NB = GIBBS_NB(KT), KEYS = 2 * KT;
     static constexpr int COMBO_FLOATS = (NB / 2) * KT * 2 + 4;          // one table of (h_j, h_j+1) pairs, + 16 bytes: the four tables start in different banks
     static constexpr size_t H_BYTES = (size_t)4 * COMBO_FLOATS * 4;     // float2 sH2[4 = bit_j + 2 bit_j+1][NB/2][KT]
     // per block of `warps` warps (rows = 32 warps): the launch sizes the dynamic shared memory with bytes(warps)
-    static constexpr size_t f_bytes(int warps) { return (size_t)warps * KT * 32 * 2; }        // ushort hF[warp][KT][32]
+    static constexpr size_t f_bytes(int warps) { return (size_t)warps * KT * 16 * 4; }        // uint   hF[warp][KT][16]: row histograms, two 16-bit counters (lanes 2i, 2i+1) per word
     static constexpr size_t k_bytes(int warps) { return (size_t)NB * 32 * warps; }            // uchar  sK[NB][rows]: key of (column, row), 0xFF = none
-    static constexpr int c_stride(int warps) { return 32 * warps + 2; }                        // ushort hC[KEYS][threads + 2]: odd word stride, no bank conflicts across keys
-    static constexpr size_t c_bytes(int warps) { return (size_t)KEYS * c_stride(warps) * 2; }
+    static constexpr size_t C_BYTES = (size_t)KEYS * NB * 4;                                   // uint   hC[KEYS][NB]: bank = column, whatever the key
     static constexpr size_t v_bytes(int warps) { return (size_t)2 * NB * warps * 4; }         // uint   sV[2][NB][warps]: value / mask bit words of the sub-tile
-    static constexpr size_t bytes(int warps) { return H_BYTES + f_bytes(warps) + k_bytes(warps) + ((c_bytes(warps) + 15) / 16) * 16 + v_bytes(warps); }
+    static constexpr size_t bytes(int warps) { return H_BYTES + f_bytes(warps) + k_bytes(warps) + C_BYTES + v_bytes(warps); }
     static constexpr size_t BYTES = bytes(GIBBS_WMAX);
 };
 
@@ -246,21 +245,21 @@ struct GibbsSweepArgs {
 };
 
 template <int KT>
-__global__ void __launch_bounds__(32 * GIBBS_WMAX) gibbs_sweep_kt_kernel(GibbsSweepArgs a)
+__global__ void __launch_bounds__(32 * GIBBS_WMAX, KT > 16 ? 2 : GIBBS_MINB16) gibbs_sweep_kt_kernel(GibbsSweepArgs a)
 {
     static_assert(KT == 4 || KT == 8 || KT == 16 || KT == 32, "KT");
     constexpr int KEYS = 2 * KT;                          // (label, bit) keys: key = 2 label + bit
     constexpr int NB = GIBBS_NB(KT);
+    static_assert((NB & (NB - 1)) == 0 && NB % 4 == 0, "NB");
     extern __shared__ __align__(16) unsigned char gsm[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nwarps = blockDim.x >> 5, nthreads = blockDim.x;
-    const int cstride = GibbsSmem<KT>::c_stride(nwarps);
     float *sH2 = reinterpret_cast<float *>(gsm);                                                      // [bit_j + 2 bit_j+1][column pair][k] (h_j, h_j+1)
     constexpr int CSF = GibbsSmem<KT>::COMBO_FLOATS;
-    unsigned short (*hF)[KT][32] = reinterpret_cast<unsigned short (*)[KT][32]>(gsm + GibbsSmem<KT>::H_BYTES);   // [warp][k][lane] private row histograms
+    uint32_t *hF = reinterpret_cast<uint32_t *>(gsm + GibbsSmem<KT>::H_BYTES);                        // [warp][k][lane / 2] packed 16-bit row counts
     unsigned char *sK = gsm + GibbsSmem<KT>::H_BYTES + GibbsSmem<KT>::f_bytes(nwarps);               // [column][row of the tile]
-    unsigned short *hC = reinterpret_cast<unsigned short *>(sK + GibbsSmem<KT>::k_bytes(nwarps));    // [key][thread], row stride cstride
-    uint32_t *sV = reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(hC) + ((GibbsSmem<KT>::c_bytes(nwarps) + 15) / 16) * 16);   // [column][warp] value words
+    uint32_t *hC = reinterpret_cast<uint32_t *>(sK + GibbsSmem<KT>::k_bytes(nwarps));                 // [key][column]
+    uint32_t *sV = hC + KEYS * NB;                                                                    // [column][warp] value words
     uint32_t *sM = sV + NB * nwarps;                                                                  // [column][warp] mask words
     const int64_t fw = (int64_t)blockIdx.y * nwarps + warp;   // bit word (32 rows) of this warp
     const int64_t f = fw * 32 + lane;
@@ -271,14 +270,15 @@ __global__ void __launch_bounds__(32 * GIBBS_WMAX) gibbs_sweep_kt_kernel(GibbsSw
     const int gwords = (8 * nwarps + groups - 1) / groups;
     const int p2col = tid % NB, p2grp = tid / NB;
     const bool p2_on = tid < NB * groups;
-#pragma unroll
-    for (int k = 0; k < KT; k++) hF[warp][k][lane] = 0;
-    for (int i = tid; i < KEYS * cstride; i += nthreads) hC[i] = 0;
-    float2 ww[KT];                                        // (w_k, w_k)
+    uint32_t *hFw = hF + (warp * KT) * 16 + (lane >> 1);  // + 16 k: this lane's counter word of component k
+    const uint32_t hFinc = 1u << (16 * (lane & 1));
+    for (int i = tid; i < nwarps * KT * 16; i += nthreads) hF[i] = 0;
+    for (int i = tid; i < KEYS * NB; i += nthreads) hC[i] = 0;
+    float w[KT];
 #pragma unroll
     for (int k4 = 0; k4 < KT; k4 += 4) {
         const float4 v = row_ok ? __ldg(reinterpret_cast<const float4 *>(a.W + f * KT + k4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        ww[k4] = make_float2(v.x, v.x); ww[k4 + 1] = make_float2(v.y, v.y); ww[k4 + 2] = make_float2(v.z, v.z); ww[k4 + 3] = make_float2(v.w, v.w);
+        w[k4] = v.x; w[k4 + 1] = v.y; w[k4 + 2] = v.z; w[k4 + 3] = v.w;
     }
     const int mis = (int)(a.n_offset & 3);                // sub-tiles start at multiples of NB: only a misaligned shard start shifts the Philox blocks
     const uint32_t pk1 = (uint32_t)(a.seed >> 32) ^ 0x2545F491u;
@@ -287,12 +287,18 @@ __global__ void __launch_bounds__(32 * GIBBS_WMAX) gibbs_sweep_kt_kernel(GibbsSw
         if (n0 >= a.N) break;                             // block-uniform
         const int nb = (int)min((int64_t)NB, a.N - n0);
         __syncthreads();                                  // the previous sub-tile's tables, keys and counts are consumed
-        for (int i = tid; i < 4 * (NB / 2) * KT; i += nthreads) {
-            const int combo = i / ((NB / 2) * KT), r = i % ((NB / 2) * KT), j = 2 * (r / KT), k = r % KT;
-            float2 hv;
-            hv.x = (j < nb) ? __ldg(a.HH + ((int64_t)(combo & 1) * a.N + n0 + j) * KT + k) : 0.f;
-            hv.y = (j + 1 < nb) ? __ldg(a.HH + ((int64_t)(combo >> 1) * a.N + n0 + j + 1) * KT + k) : 0.f;
-            *reinterpret_cast<float2 *>(sH2 + combo * CSF + 2 * r) = hv;
+        // the four tables of every column pair from four loads: (H or 1-H of column j, H or 1-H of column j+1)
+        for (int i = tid; i < (NB / 2) * KT; i += nthreads) {
+            const int j = 2 * (i / KT), k = i % KT;
+            float h[2][2];                                // [column j / j+1][bit]
+#pragma unroll
+            for (int c = 0; c < 2; c++)
+#pragma unroll
+                for (int b = 0; b < 2; b++)
+                    h[c][b] = (j + c < nb) ? __ldg(a.HH + ((int64_t)b * a.N + n0 + j + c) * KT + k) : 0.f;
+#pragma unroll
+            for (int combo = 0; combo < 4; combo++)
+                *reinterpret_cast<float2 *>(sH2 + combo * CSF + 2 * i) = make_float2(h[0][combo & 1], h[1][combo >> 1]);
         }
         // the sub-tile's bit words, fetched once by the block (a load per column right before its use stalled every warp
         // for an L2 round trip: 28 % of the stall samples of the first version); columns beyond the matrix: no bits
@@ -304,13 +310,19 @@ __global__ void __launch_bounds__(32 * GIBBS_WMAX) gibbs_sweep_kt_kernel(GibbsSw
             sM[i] = in ? (a.mc ? __ldg(a.mc + (n0 + j) * a.Fw + wrd) : 0xffffffffu) : 0u;
         }
         __syncthreads();
-        // ---- phase 1: thread = row, loop over the sub-tile's columns, two at a time
+        // ---- phase 1: thread = row, four columns (one Philox block, two column pairs) per iteration.  Columns beyond
+        //      the matrix have no bits and all-zero tables: they are sampled like the rest and never counted.
         for (int j0 = 0; j0 < nb; j0 += 4) {
+            if (!word_ok) {                               // warp-uniform: rows beyond the matrix leave empty keys
+#pragma unroll
+                for (int jj = 0; jj < 4; jj++) sK[(j0 + jj) * nthreads + tid] = 0xFF;
+                continue;
+            }
             // one Philox block per four consecutive GLOBAL columns (keyed by the global column, so the
             // chain does not depend on the sharding); a misaligned shard start straddles two blocks
             const int64_t ng0 = n0 + j0 + a.n_offset;
-            uint32_t rnd[4] = {0u, 0u, 0u, 0u};
-            if (word_ok) {
+            uint32_t rnd[4];
+            {
                 const philox4 ra = philox4x32_10((uint32_t)f, (uint32_t)(ng0 >> 2), (uint32_t)(ng0 >> 34), a.sweep, (uint32_t)a.seed, pk1);
                 rnd[0] = ra.x; rnd[1] = ra.y; rnd[2] = ra.z; rnd[3] = ra.w;
                 if (mis) {                                // warp-uniform, sharded runs only
@@ -320,51 +332,53 @@ __global__ void __launch_bounds__(32 * GIBBS_WMAX) gibbs_sweep_kt_kernel(GibbsSw
                     for (int jj = 0; jj < 4; jj++) rnd[jj] = mis == 1 ? all[jj + 1] : mis == 2 ? all[jj + 2] : all[jj + 3];
                 }
             }
+            uint32_t vw[4], mw[4];
 #pragma unroll
-            for (int pp = 0; pp < 2; pp++) {
+            for (int jj = 0; jj < 4; jj++) { vw[jj] = sV[(j0 + jj) * nwarps + warp]; mw[jj] = sM[(j0 + jj) * nwarps + warp]; }
+            int kz[4];
+            auto sample_pair = [&](const int pp, int &kz_a, int &kz_b) {
                 const int j = j0 + 2 * pp;                // columns j and j + 1
-                if (j >= nb) break;                       // block-uniform
-                int key0 = 0xFF, key1 = 0xFF;
-                if (word_ok) {
-                    const uint32_t vw0 = sV[j * nwarps + warp], vw1 = sV[(j + 1) * nwarps + warp];
-                    const uint32_t mw0 = sM[j * nwarps + warp], mw1 = sM[(j + 1) * nwarps + warp];
-                    const bool obs0 = row_ok && ((mw0 >> lane) & 1u), obs1 = row_ok && ((mw1 >> lane) & 1u);
-                    const int v0 = (vw0 >> lane) & 1u, v1 = (vw1 >> lane) & 1u;
-                    const float4 *hp = reinterpret_cast<const float4 *>(sH2 + (v0 + 2 * v1) * CSF + (j >> 1) * (2 * KT));
-                    float2 c[KT];
-                    float2 run = make_float2(0.f, 0.f);
+                const int v0 = (vw[2 * pp] >> lane) & 1u, v1 = (vw[2 * pp + 1] >> lane) & 1u;
+                const float4 *hp = reinterpret_cast<const float4 *>(sH2 + (v0 + 2 * v1) * CSF + (j >> 1) * (2 * KT));
+                float2 c[KT];
+                float2 run = make_float2(0.f, 0.f);
 #pragma unroll
-                    for (int k2 = 0; k2 < KT; k2 += 2) {
-                        const float4 h4 = hp[k2 >> 1];    // (h_j[k2], h_j+1[k2], h_j[k2+1], h_j+1[k2+1])
-                        run = __ffma2_rn(ww[k2], make_float2(h4.x, h4.y), run); c[k2] = run;
-                        run = __ffma2_rn(ww[k2 + 1], make_float2(h4.z, h4.w), run); c[k2 + 1] = run;
-                    }
-                    const float2 target = __fmul2_rn(make_float2(u24(rnd[2 * pp]), u24(rnd[2 * pp + 1])), run);
-                    // inverse CDF without a second pass: the label is the number of running sums at or
-                    // below the target (they are non-decreasing; u < 1 keeps it below the last one, and
-                    // a padded component repeats the last sum, so it is never drawn)
-                    // counted in fp32 pairs on top of 2^23, where one ulp is 1: the low mantissa bits are the count
-                    float2 n_a = make_float2(8388608.f, 8388608.f), n_b = make_float2(0.f, 0.f);
-#pragma unroll
-                    for (int k = 0; k < KT - 1; k++) {
-                        const float2 one = make_float2(le_one(c[k].x, target.x), le_one(c[k].y, target.y));
-                        if (k & 1) n_b = __fadd2_rn(n_b, one); else n_a = __fadd2_rn(n_a, one);
-                    }
-                    n_a = __fadd2_rn(n_a, n_b);
-                    const int kz0 = min(__float_as_int(n_a.x) & 0xFF, a.K - 1), kz1 = min(__float_as_int(n_a.y) & 0xFF, a.K - 1);
-                    if (obs0) { hF[warp][kz0][lane] += 1; key0 = 2 * kz0 + v0; }
-                    if (obs1) { hF[warp][kz1][lane] += 1; key1 = 2 * kz1 + v1; }
-                    if (a.Zout && row_ok) {
-                        a.Zout[f + a.F * (n0 + j)] = obs0 ? kz0 : NBMF_NA_INTEGER;
-                        if (j + 1 < nb) a.Zout[f + a.F * (n0 + j + 1)] = obs1 ? kz1 : NBMF_NA_INTEGER;
-                    }
+                for (int k2 = 0; k2 < KT; k2 += 2) {
+                    const float4 h4 = hp[k2 >> 1];        // (h_j[k2], h_j+1[k2], h_j[k2+1], h_j+1[k2+1])
+                    run = __ffma2_rn(make_float2(w[k2], w[k2]), make_float2(h4.x, h4.y), run); c[k2] = run;
+                    run = __ffma2_rn(make_float2(w[k2 + 1], w[k2 + 1]), make_float2(h4.z, h4.w), run); c[k2 + 1] = run;
                 }
-                sK[j * nthreads + tid] = (unsigned char)key0;
-                sK[(j + 1) * nthreads + tid] = (unsigned char)key1;
+                const float2 target = __fmul2_rn(make_float2(u24(rnd[2 * pp]), u24(rnd[2 * pp + 1])), run);
+                // inverse CDF without a second pass: the label is the number of running sums at or
+                // below the target (they are non-decreasing; u < 1 keeps it below the last one, and
+                // a padded component repeats the last sum, so it is never drawn);
+                // counted in fp32 pairs on top of 2^23, where one ulp is 1: the low mantissa bits are the count
+                float2 n_a = make_float2(8388608.f, 8388608.f), n_b = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int k = 0; k < KT - 1; k++) {
+                    const float2 one = make_float2(le_one(c[k].x, target.x), le_one(c[k].y, target.y));
+                    if (k & 1) n_b = __fadd2_rn(n_b, one); else n_a = __fadd2_rn(n_a, one);
+                }
+                n_a = __fadd2_rn(n_a, n_b);
+                kz_a = min(__float_as_int(n_a.x) & 0xFF, a.K - 1);
+                kz_b = min(__float_as_int(n_a.y) & 0xFF, a.K - 1);
+            };
+            // both pairs in flight while their running sums fit the registers; one after the other at K > 16
+            sample_pair(0, kz[0], kz[1]);
+            if (KT > 16) __syncwarp();
+            sample_pair(1, kz[2], kz[3]);
+#pragma unroll
+            for (int jj = 0; jj < 4; jj++) {
+                const bool obs = row_ok && ((mw[jj] >> lane) & 1u);
+                const int v = (vw[jj] >> lane) & 1u;
+                if (obs) atomicAdd(hFw + 16 * kz[jj], hFinc);     // the lane's own 16-bit counter: no return value, no dependency
+                sK[(j0 + jj) * nthreads + tid] = (unsigned char)(obs ? 2 * kz[jj] + v : 0xFF);
+                if (a.Zout && row_ok && j0 + jj < nb) a.Zout[f + a.F * (n0 + j0 + jj)] = obs ? kz[jj] : NBMF_NA_INTEGER;
             }
         }
         __syncthreads();
-        // ---- phase 2: thread = (column, row group): the column's keys into the thread's private histogram column
+        // ---- phase 2: thread = (column, row group): the column's keys into the column's counters (bank = column, so a
+        //      warp's 32 columns never conflict; the row groups of a column meet in the atomic unit)
         if (p2_on && p2col < nb) {
             const uint32_t *kw = reinterpret_cast<const uint32_t *>(sK + p2col * nthreads);
             const int w0 = p2grp * gwords, w1 = min(8 * nwarps, w0 + gwords);
@@ -373,26 +387,29 @@ __global__ void __launch_bounds__(32 * GIBBS_WMAX) gibbs_sweep_kt_kernel(GibbsSw
 #pragma unroll
                 for (int b = 0; b < 4; b++) {
                     const uint32_t key = (kk >> (8 * b)) & 0xFFu;
-                    if (key != 0xFFu) hC[key * cstride + tid] += 1;
+                    if (key != 0xFFu) atomicAdd(hC + key * NB + p2col, 1u);
                 }
             }
         }
         __syncthreads();
-        // column-side counts of the sub-tile: sum over the row groups, out to (2n + bit, label); clear for the next one
-        for (int i = tid; i < nb * KEYS; i += nthreads) {
-            const int j = i % nb, kk = i / nb;            // consecutive threads: consecutive columns (bank = column)
-            int cnt = 0;
-            for (int g = 0; g < groups; g++) { cnt += (int)hC[kk * cstride + g * NB + j]; hC[kk * cstride + g * NB + j] = 0; }
-            const int64_t idx = (2 * (n0 + j) + (kk & 1)) * KT + (kk >> 1);
-            if (a.cn_atomic) { if (cnt) atomicAdd(a.cNp + idx, cnt); }
-            else a.cNp[(int64_t)blockIdx.y * 2 * a.N * KT + idx] = cnt;
+        // column-side counts of the sub-tile out to (2n + bit, label); clear for the next one
+        for (int i = tid; i < NB * KEYS; i += nthreads) {
+            const int j = i & (NB - 1), kk = i / NB;      // consecutive threads: consecutive columns (bank = column)
+            const int cnt = (int)hC[i];
+            hC[i] = 0;
+            if (j < nb) {
+                const int64_t idx = (2 * (n0 + j) + (kk & 1)) * KT + (kk >> 1);
+                if (a.cn_atomic) { if (cnt) atomicAdd(a.cNp + idx, cnt); }
+                else a.cNp[(int64_t)blockIdx.y * 2 * a.N * KT + idx] = cnt;
+            }
         }
     }
+    __syncthreads();
     // row-side counts of the block's columns
     if (row_ok) {
 #pragma unroll
         for (int k = 0; k < KT; k++) {
-            const int cnt = (int)hF[warp][k][lane];
+            const int cnt = (int)((hFw[16 * k] >> (16 * (lane & 1))) & 0xFFFFu);
             if (cnt) atomicAdd(a.cF + f * KT + k, cnt);
         }
     }

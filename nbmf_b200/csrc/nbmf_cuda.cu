@@ -1241,6 +1241,16 @@ static cudaError_t launch_gibbs_sweep(const GibbsSweepArgs &a, dim3 grid, int wa
     return cudaGetLastError();
 }
 
+template <int KT>
+static int gibbs_sweep_occupancy(int warps)   // resident blocks per SM
+{
+    int occ = 0;
+    cudaFuncSetAttribute(gibbs_sweep_kt_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GibbsSmem<KT>::BYTES);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gibbs_sweep_kt_kernel<KT>, 32 * warps, GibbsSmem<KT>::bytes(warps));
+    cudaGetLastError();
+    return occ;
+}
+
 // Uncollapsed blocked chain, K <= 32: two launches per sweep (gibbs_fast.cuh).  Sweep i draws W, H from
 // the counts of sweep i-1, then samples every entry; a kept sweep (i >= floor(iter * burnin), the
 // reference's bookkeeping, collapsed_gibbs_z.cpp:423-426) adds the Rao-Blackwell means of ITS counts,
@@ -1314,7 +1324,26 @@ static int gibbs_dirber_fast(nbmf_handle *h, int K, double alpha, double beta, d
     // enough blocks for a few waves of 148 SMs, each amortising its row histograms over ct sub-tiles
     const int NBc = GIBBS_NB(KT);
     const int64_t n_tiles = (N + NBc - 1) / NBc;
-    int ct = (int)std::max<int64_t>(1, std::min<int64_t>(GIBBS_CT_MAX, (n_tiles * f_tiles) / (6ll * h->sm_count)));
+    // sub-tiles per block: the grid should fill whole waves of resident blocks (a block costs its ct sub-tiles plus
+    // about a third of one for its row histograms and weights)
+    int ct = 1;
+    {
+        int occ = 0;
+        switch (KT) {
+        case 4: occ = gibbs_sweep_occupancy<4>(warps); break;
+        case 8: occ = gibbs_sweep_occupancy<8>(warps); break;
+        case 16: occ = gibbs_sweep_occupancy<16>(warps); break;
+        default: occ = gibbs_sweep_occupancy<32>(warps); break;
+        }
+        cudaGetLastError();
+        const int64_t cap = (int64_t)std::max(1, occ) * h->sm_count;
+        double best = 0;
+        for (int c = 1; c <= GIBBS_CT_MAX; c++) {
+            const int64_t blocks = ((n_tiles + c - 1) / c) * f_tiles;
+            const double cost = (double)((blocks + cap - 1) / cap) * (c + 0.35);
+            if (c == 1 || cost < best) { best = cost; ct = c; }
+        }
+    }
     sw.ct = ct;
     const dim3 sgrid((unsigned)((n_tiles + ct - 1) / ct), (unsigned)f_tiles);
     const unsigned dgrid = nblk((F + (N + 32 / KT - 1) / (32 / KT)) * 32, 256);   // a warp per row, a warp per 32 / KT columns

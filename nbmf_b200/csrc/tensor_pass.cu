@@ -38,6 +38,10 @@
 #include <cstdlib>
 
 #define TP_THREADS 640
+#ifndef TP_REGS_SERVICE
+#define TP_REGS_SERVICE 32   // 128 x (96 - 32) registers released ...
+#define TP_REGS_EPI 112      // ... 512 x (112 - 96) taken (the pool is the 640 x 96 of the launch)
+#endif
 // failed barrier probes before a role gives up and raises the abort flag (about 0.1 s at the
 // default; a debugger, compute-sanitizer or a heavy ncu replay may need more: NBMF_TP_SPIN_LIMIT)
 __constant__ uint32_t c_tp_spin_limit = 1u << 20;
@@ -478,6 +482,13 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar)
 {
     asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(bar) : "memory");
 }
+// arrive and return the low word of the barrier's state: a value that only exists once the arrive has executed
+__device__ __forceinline__ uint32_t mbar_arrive_token(uint32_t bar)
+{
+    uint64_t st;
+    asm volatile("mbarrier.arrive.shared::cta.b64 %0, [%1];" : "=l"(st) : "r"(bar) : "memory");
+    return (uint32_t)st;
+}
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
 {
     asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"(bar), "r"(bytes)
@@ -574,6 +585,21 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32])
                    "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                  : "r"(taddr));
 }
+__device__ __forceinline__ void tc_ld64(uint32_t taddr, uint32_t (&r)[64])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x64.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]), "=r"(r[48]), "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]), "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+                 : "r"(taddr));
+}
+// register budget per role (setmaxnreg acts on a warpgroup = four consecutive warps): the four service warps give
+// most of their launch-time registers back, the epilogue warpgroups take them
+#ifndef TP_NO_SETMAXNREG
+template <int N> __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+#else
+template <int N> __device__ __forceinline__ void reg_dealloc() {}
+template <int N> __device__ __forceinline__ void reg_alloc() {}
+#endif
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&r)[16])
@@ -701,7 +727,7 @@ struct TPCfg {
     static constexpr int STAGES = (224 * 1024 / TILE_BYTES) > 16 ? 16 : (224 * 1024 / TILE_BYTES);
     // S slots (fp32 stage-1 accumulators, 64 columns each).  The e5m2 copy of R needs 64 more TMEM
     // columns: at KP = 128 an S slot makes room (a step is longer there, two slots keep stage 1 fed).
-    static constexpr int NS = (LO8 && KP == 128) ? 2 : 3;
+    static constexpr int NS = (LO8 && KP == 128) ? 2 : ((KP == 64 && !LO8) ? 4 : 3);   // KP = 64 has TMEM to spare: a fourth slot
     static constexpr int NR = 4;                            // R slots (f16 reciprocals, 32 columns each)
     static constexpr int COL_G = 0;
     static constexpr int COL_S = KP;                        // + 64 * (step % NS)
@@ -780,8 +806,12 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
     const int eU = ROWS ? a.dexp[0] : a.dexp[1];
     const int eW = ROWS ? a.dexp[1] : a.dexp[0];
 
+    // 640 threads x 96 registers at launch; the service warpgroup keeps TP_REGS_SERVICE, each epilogue thread gets
+    // TP_REGS_EPI: enough to hold a whole S tile (64 columns) next to the packed results, so that the S slot goes
+    // back to the stage-1 issuer one TMEM-load latency after stage 1 completed
     if (warp == 0) {
         // ===================== TMA producer =====================
+        reg_dealloc<TP_REGS_SERVICE>();
         if (elect_one()) {
             uint32_t stage = 0, phase = 0;
             PROF_DECL;
@@ -828,6 +858,7 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
         // (no indexed arrays) and descriptors are formed as {base_lo + constant, constant_hi}.
         // A wait on the parity *before* a barrier's first completion returns at once, which
         // covers the first use of every slot.
+        reg_dealloc<TP_REGS_SERVICE>();
         if (elect_one()) {
             constexpr uint32_t IDESC1 = make_idesc(128, C::STEP_ROWS, 0);
             constexpr uint32_t DHI = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO = 1024 B, version 1, SWIZZLE_128B
@@ -878,6 +909,7 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
         }
     } else if (warp == 3) {
         // ===================== MMA issuer, stage 2: G += R(slot gs%4) . (W_hi [+ W_lo]) =====================
+        reg_dealloc<TP_REGS_SERVICE>();
         if (elect_one()) {
             constexpr uint32_t IDESC2 = make_idesc(128, KP, 1);
             constexpr uint32_t DHI = (1024u >> 4) | (1u << 14) | (2u << 29);
@@ -952,8 +984,11 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
             }
             PROF_OUT(2);
         }
-    } else if (warp >= 4) {
+    } else if (warp == 2) {
+        reg_dealloc<TP_REGS_SERVICE>();   // (the TMEM allocator warp: setmaxnreg is a warpgroup-wide instruction)
+    } else {
         // ===================== epilogue =====================
+        reg_alloc<TP_REGS_EPI>();
         // four warpgroups; group g owns R slot g and handles the steps with gs = g (mod 4).  More
         // resident warps than the arithmetic needs: one step's epilogue (TMEM load -> select ->
         // rcp -> pack -> TMEM store -> mbarrier) lasts about two tensor steps.
@@ -977,6 +1012,7 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
         PROF_DECL;
         const float c0 = exp2f((float)(eU + eW - 14));
         const float c1 = exp2f((float)(-(eU + eW)));   // S * c1 = D: lg2.approx's relative error must apply to log2 D, not to log2 S
+        const uint32_t zmask = ((uint32_t)a.dbg_flags & 0x40000000u) ? 0xffffffffu : 0u;   // always 0 (no experiment uses the bit)
         const float fhuge = __int_as_float(0x5f800000);   // 2^64: stand-in for an unselected entry
         const float ftiny = __int_as_float(0x21800000);   // 2^-60: keeps the shared reciprocal finite when S underflowed to 0
         double log_acc_total = 0.0;
@@ -1152,16 +1188,34 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
                 ok = ok && mbar_wait(bar_sfull, r_par, abort_flag, 8);
                 tc_fence_after();
                 PROF_ACC(2);
-                // both halves of S are loaded before any arithmetic so that the slot goes back to the
-                // stage-1 issuer one TMEM-load latency after stage 1 completed
+                // Two ways of reading the S tile.  With only two S slots (hi + e5m2 lo at KP = 128) the slot is the
+                // scarce resource: one 64-column load, the slot handed back BEFORE any arithmetic -- ptxas would otherwise
+                // hoist the first sixty-odd instructions above the arrive (they only depend on the load), so the
+                // selection bits are tied to the arrive's return value (tz = 0 at run time, unknown at compile time).
+                // With three or four slots the group's own latency is what counts: two 32-column loads, the arithmetic
+                // starts when the first has landed and the slot goes back when both have.
                 uint32_t s0[32], s1[32], rp0[16], rp1[16];
-                tc_ld32(t_s, s0);
-                tc_ld32(t_s + 32, s1);
-                // stage 2 of step gs-4 must be done with the R slot: probe now, look at the answer later
-                const uint32_t rfree = mbar_try(bar_rfree, r_par ^ 1u);
-                tc_wait_ld();
-                tc_fence_before();
-                mbar_arrive(BAR_SFREE + 8u * sslot);
+                uint32_t rfree;
+                if constexpr (C::NS == 2) {
+                    uint32_t sa[64];
+                    tc_ld64(t_s, sa);
+                    // stage 2 of step gs-4 must be done with the R slot: probe now, look at the answer later
+                    rfree = mbar_try(bar_rfree, r_par ^ 1u);
+                    tc_wait_ld();
+                    tc_fence_before();
+                    const uint32_t tz = mbar_arrive_token(BAR_SFREE + 8u * sslot) & zmask;
+#pragma unroll
+                    for (int i = 0; i < WPS; i++) { sel[i] ^= tz; vv[i] ^= tz; }
+#pragma unroll
+                    for (int i = 0; i < 32; i++) { s0[i] = sa[i]; s1[i] = sa[32 + i]; }
+                } else {
+                    tc_ld32(t_s, s0);
+                    tc_ld32(t_s + 32, s1);
+                    rfree = mbar_try(bar_rfree, r_par ^ 1u);
+                    tc_wait_ld();
+                    tc_fence_before();
+                    mbar_arrive(BAR_SFREE + 8u * sslot);
+                }
 #ifdef TP_DEBUG_DUMP
                 if (a.dbg != nullptr && w == 0 && t < 4)
                     for (int i = 0; i < 32; i++) {
