@@ -244,7 +244,7 @@ struct GibbsSweepArgs {
     int32_t *Zout;              // F x N labels of this sweep, or NULL
 };
 
-template <int KT>
+template <int KT, bool MASKED>   // MASKED: the matrix has missing entries (mask plane mc)
 __global__ void __launch_bounds__(32 * GIBBS_WMAX, KT > 16 ? 2 : GIBBS_MINB16) gibbs_sweep_kt_kernel(GibbsSweepArgs a)
 {
     static_assert(KT == 4 || KT == 8 || KT == 16 || KT == 32, "KT");
@@ -259,8 +259,8 @@ __global__ void __launch_bounds__(32 * GIBBS_WMAX, KT > 16 ? 2 : GIBBS_MINB16) g
     uint32_t *hF = reinterpret_cast<uint32_t *>(gsm + GibbsSmem<KT>::H_BYTES);                        // [warp][k][lane / 2] packed 16-bit row counts
     unsigned char *sK = gsm + GibbsSmem<KT>::H_BYTES + GibbsSmem<KT>::f_bytes(nwarps);               // [column][row of the tile]
     uint32_t *hC = reinterpret_cast<uint32_t *>(sK + GibbsSmem<KT>::k_bytes(nwarps));                 // [key][column]
-    uint32_t *sV = hC + KEYS * NB;                                                                    // [column][warp] value words
-    uint32_t *sM = sV + NB * nwarps;                                                                  // [column][warp] mask words
+    uint32_t *sV = hC + KEYS * NB;                                                                    // [warp][column] value words
+    uint32_t *sM = sV + NB * nwarps;                                                                  // [warp][column] mask words (MASKED)
     const int64_t fw = (int64_t)blockIdx.y * nwarps + warp;   // bit word (32 rows) of this warp
     const int64_t f = fw * 32 + lane;
     const bool row_ok = f < a.F;
@@ -303,11 +303,11 @@ __global__ void __launch_bounds__(32 * GIBBS_WMAX, KT > 16 ? 2 : GIBBS_MINB16) g
         // the sub-tile's bit words, fetched once by the block (a load per column right before its use stalled every warp
         // for an L2 round trip: 28 % of the stall samples of the first version); columns beyond the matrix: no bits
         for (int i = tid; i < NB * nwarps; i += nthreads) {
-            const int j = i / nwarps, wq = i % nwarps;
+            const int j = i % NB, wq = i / NB;
             const int64_t wrd = (int64_t)blockIdx.y * nwarps + wq;
             const bool in = wrd < a.Fw && j < nb;
             sV[i] = in ? __ldg(a.vc + (n0 + j) * a.Fw + wrd) : 0u;
-            sM[i] = in ? (a.mc ? __ldg(a.mc + (n0 + j) * a.Fw + wrd) : 0xffffffffu) : 0u;
+            if (MASKED) sM[i] = in ? __ldg(a.mc + (n0 + j) * a.Fw + wrd) : 0u;
         }
         __syncthreads();
         // ---- phase 1: thread = row, four columns (one Philox block, two column pairs) per iteration.  Columns beyond
@@ -332,9 +332,14 @@ __global__ void __launch_bounds__(32 * GIBBS_WMAX, KT > 16 ? 2 : GIBBS_MINB16) g
                     for (int jj = 0; jj < 4; jj++) rnd[jj] = mis == 1 ? all[jj + 1] : mis == 2 ? all[jj + 2] : all[jj + 3];
                 }
             }
-            uint32_t vw[4], mw[4];
-#pragma unroll
-            for (int jj = 0; jj < 4; jj++) { vw[jj] = sV[(j0 + jj) * nwarps + warp]; mw[jj] = sM[(j0 + jj) * nwarps + warp]; }
+            // the four columns' bit words of this warp: one 128-bit load each for values and mask
+            const uint4 vq = *reinterpret_cast<const uint4 *>(sV + warp * NB + j0);
+            const uint32_t vw[4] = {vq.x, vq.y, vq.z, vq.w};
+            uint32_t mw[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+            if (MASKED) {
+                const uint4 mq = *reinterpret_cast<const uint4 *>(sM + warp * NB + j0);
+                mw[0] = mq.x; mw[1] = mq.y; mw[2] = mq.z; mw[3] = mq.w;
+            }
             int kz[4];
             auto sample_pair = [&](const int pp, int &kz_a, int &kz_b) {
                 const int j = j0 + 2 * pp;                // columns j and j + 1
@@ -348,7 +353,10 @@ __global__ void __launch_bounds__(32 * GIBBS_WMAX, KT > 16 ? 2 : GIBBS_MINB16) g
                     run = __ffma2_rn(make_float2(w[k2], w[k2]), make_float2(h4.x, h4.y), run); c[k2] = run;
                     run = __ffma2_rn(make_float2(w[k2 + 1], w[k2 + 1]), make_float2(h4.z, h4.w), run); c[k2 + 1] = run;
                 }
-                const float2 target = __fmul2_rn(make_float2(u24(rnd[2 * pp]), u24(rnd[2 * pp + 1])), run);
+                // target = u total with u = ((x >> 9) + 1/2) 2^-23 (u24): one rounding, as u24(x) * total
+                const float2 rs = __fmul2_rn(run, make_float2(1.0f / 8388608.0f, 1.0f / 8388608.0f));
+                const float2 target = __ffma2_rn(make_float2((float)(rnd[2 * pp] >> 9), (float)(rnd[2 * pp + 1] >> 9)), rs,
+                                                 __fmul2_rn(rs, make_float2(0.5f, 0.5f)));
                 // inverse CDF without a second pass: the label is the number of running sums at or
                 // below the target (they are non-decreasing; u < 1 keeps it below the last one, and
                 // a padded component repeats the last sum, so it is never drawn);
@@ -369,7 +377,7 @@ __global__ void __launch_bounds__(32 * GIBBS_WMAX, KT > 16 ? 2 : GIBBS_MINB16) g
             sample_pair(1, kz[2], kz[3]);
 #pragma unroll
             for (int jj = 0; jj < 4; jj++) {
-                const bool obs = row_ok && ((mw[jj] >> lane) & 1u);
+                const bool obs = MASKED ? (row_ok && ((mw[jj] >> lane) & 1u)) : (row_ok && j0 + jj < nb);
                 const int v = (vw[jj] >> lane) & 1u;
                 if (obs) atomicAdd(hFw + 16 * kz[jj], hFinc);     // the lane's own 16-bit counter: no return value, no dependency
                 sK[(j0 + jj) * nthreads + tid] = (unsigned char)(obs ? 2 * kz[jj] + v : 0xFF);

@@ -1235,9 +1235,16 @@ extern "C" int nbmf_vb_dirber(nbmf_handle *h, int K, double alpha, double beta, 
 template <int KT>
 static cudaError_t launch_gibbs_sweep(const GibbsSweepArgs &a, dim3 grid, int warps, cudaStream_t st)
 {
-    cudaError_t e = cudaFuncSetAttribute(gibbs_sweep_kt_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GibbsSmem<KT>::BYTES);
-    if (e != cudaSuccess) return e;
-    gibbs_sweep_kt_kernel<KT><<<grid, 32 * warps, GibbsSmem<KT>::bytes(warps), st>>>(a);
+    cudaError_t e;
+    if (a.mc) {
+        e = cudaFuncSetAttribute(gibbs_sweep_kt_kernel<KT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GibbsSmem<KT>::BYTES);
+        if (e != cudaSuccess) return e;
+        gibbs_sweep_kt_kernel<KT, true><<<grid, 32 * warps, GibbsSmem<KT>::bytes(warps), st>>>(a);
+    } else {
+        e = cudaFuncSetAttribute(gibbs_sweep_kt_kernel<KT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GibbsSmem<KT>::BYTES);
+        if (e != cudaSuccess) return e;
+        gibbs_sweep_kt_kernel<KT, false><<<grid, 32 * warps, GibbsSmem<KT>::bytes(warps), st>>>(a);
+    }
     return cudaGetLastError();
 }
 
@@ -1245,8 +1252,11 @@ template <int KT>
 static int gibbs_sweep_occupancy(int warps)   // resident blocks per SM
 {
     int occ = 0;
-    cudaFuncSetAttribute(gibbs_sweep_kt_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GibbsSmem<KT>::BYTES);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gibbs_sweep_kt_kernel<KT>, 32 * warps, GibbsSmem<KT>::bytes(warps));
+    // the whole shared-memory carve-out: the resident block count is set by shared memory and registers, not by L1
+    cudaFuncSetAttribute(gibbs_sweep_kt_kernel<KT, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(gibbs_sweep_kt_kernel<KT, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(gibbs_sweep_kt_kernel<KT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GibbsSmem<KT>::BYTES);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gibbs_sweep_kt_kernel<KT, false>, 32 * warps, GibbsSmem<KT>::bytes(warps));
     cudaGetLastError();
     return occ;
 }
