@@ -286,7 +286,9 @@ __global__ void __launch_bounds__(32 * GIBBS_WMAX, KT > 16 ? 2 : GIBBS_MINB16) g
         const int64_t n0 = ((int64_t)blockIdx.x * a.ct + st) * NB;
         if (n0 >= a.N) break;                             // block-uniform
         const int nb = (int)min((int64_t)NB, a.N - n0);
-        __syncthreads();                                  // the previous sub-tile's tables, keys and counts are consumed
+        // (No barrier here: the previous sub-tile's tables were last read before its post-phase-1 barrier, its keys before
+        // the post-phase-2 barrier, and its counters are read below by the loop that ran right after that barrier; all
+        // three are next written behind at least one more barrier.  The table build overlaps the count output.)
         // the four tables of every column pair from four loads: (H or 1-H of column j, H or 1-H of column j+1)
         for (int i = tid; i < (NB / 2) * KT; i += nthreads) {
             const int j = 2 * (i / KT), k = i % KT;

@@ -806,12 +806,14 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
     const int eU = ROWS ? a.dexp[0] : a.dexp[1];
     const int eW = ROWS ? a.dexp[1] : a.dexp[0];
 
-    // 640 threads x 96 registers at launch; the service warpgroup keeps TP_REGS_SERVICE, each epilogue thread gets
-    // TP_REGS_EPI: enough to hold a whole S tile (64 columns) next to the packed results, so that the S slot goes
-    // back to the stage-1 issuer one TMEM-load latency after stage 1 completed
+    // Register budgets per role, for the variant with two S slots (hi + e5m2 lo at KP = 128), whose epilogue holds a whole
+    // S tile (64 columns) next to the packed results: 640 threads x 96 registers at launch; the service warpgroup keeps
+    // TP_REGS_SERVICE, each epilogue thread gets TP_REGS_EPI.  The other variants read S in two halves and fit the 96
+    // of the launch; there the service warps' spills (one local load per step in the stage-1 issuer) cost more than the
+    // epilogue gains (measured: C4 5.07 -> 5.20 ms, C5 hi-only +1 %).
     if (warp == 0) {
         // ===================== TMA producer =====================
-        reg_dealloc<TP_REGS_SERVICE>();
+        if constexpr (C::NS == 2) reg_dealloc<TP_REGS_SERVICE>();
         if (elect_one()) {
             uint32_t stage = 0, phase = 0;
             PROF_DECL;
@@ -858,7 +860,7 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
         // (no indexed arrays) and descriptors are formed as {base_lo + constant, constant_hi}.
         // A wait on the parity *before* a barrier's first completion returns at once, which
         // covers the first use of every slot.
-        reg_dealloc<TP_REGS_SERVICE>();
+        if constexpr (C::NS == 2) reg_dealloc<TP_REGS_SERVICE>();
         if (elect_one()) {
             constexpr uint32_t IDESC1 = make_idesc(128, C::STEP_ROWS, 0);
             constexpr uint32_t DHI = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO = 1024 B, version 1, SWIZZLE_128B
@@ -909,7 +911,7 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
         }
     } else if (warp == 3) {
         // ===================== MMA issuer, stage 2: G += R(slot gs%4) . (W_hi [+ W_lo]) =====================
-        reg_dealloc<TP_REGS_SERVICE>();
+        if constexpr (C::NS == 2) reg_dealloc<TP_REGS_SERVICE>();
         if (elect_one()) {
             constexpr uint32_t IDESC2 = make_idesc(128, KP, 1);
             constexpr uint32_t DHI = (1024u >> 4) | (1u << 14) | (2u << 29);
@@ -985,10 +987,10 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
             PROF_OUT(2);
         }
     } else if (warp == 2) {
-        reg_dealloc<TP_REGS_SERVICE>();   // (the TMEM allocator warp: setmaxnreg is a warpgroup-wide instruction)
+        if constexpr (C::NS == 2) reg_dealloc<TP_REGS_SERVICE>();   // (the TMEM allocator warp: setmaxnreg is a warpgroup-wide instruction)
     } else {
         // ===================== epilogue =====================
-        reg_alloc<TP_REGS_EPI>();
+        if constexpr (C::NS == 2) reg_alloc<TP_REGS_EPI>();
         // four warpgroups; group g owns R slot g and handles the steps with gs = g (mod 4).  More
         // resident warps than the arithmetic needs: one step's epilogue (TMEM load -> select ->
         // rcp -> pack -> TMEM store -> mbarrier) lasts about two tensor steps.
