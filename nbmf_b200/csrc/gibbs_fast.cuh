@@ -77,7 +77,7 @@ struct PhiloxF {   // fp32 draws from a keyed Philox stream (same keying scheme 
     __device__ float normal()
     {
         const float u = unif(), v = unif();
-        return sqrtf(-2.0f * logf(u)) * cospif(2.0f * v);
+        return sqrtf(-2.0f * __logf(u)) * __cosf(6.2831853071795864f * v);   // MUFU forms: 1e-6 is far below the sampler's resolution
     }
     // Marsaglia-Tsang; shape < 1 through Gamma(a+1) U^(1/a) (gamma = 1/K priors with empty counts).
     // The boost is returned as a logarithm so that a Dirichlet row can be normalised without
@@ -85,7 +85,7 @@ struct PhiloxF {   // fp32 draws from a keyed Philox stream (same keying scheme 
     __device__ float gamma_log(float a, float *logboost)
     {
         *logboost = 0.f;
-        if (a < 1.0f) { *logboost = logf(unif()) / a; a += 1.0f; }
+        if (a < 1.0f) { *logboost = __logf(unif()) / a; a += 1.0f; }
         const float d = a - 1.0f / 3.0f, c = rsqrtf(9.0f * d);
         for (int it = 0; it < 64; it++) {
             const float x = normal();
@@ -95,7 +95,7 @@ struct PhiloxF {   // fp32 draws from a keyed Philox stream (same keying scheme 
             const float u = unif();
             const float x2 = x * x;
             if (u < 1.0f - 0.0331f * x2 * x2) return d * v;
-            if (logf(u) < 0.5f * x2 + d * (1.0f - v + logf(v))) return d * v;
+            if (__logf(u) < 0.5f * x2 + d * (1.0f - v + __logf(v))) return d * v;
         }
         return d;
     }
@@ -151,11 +151,11 @@ __global__ void __launch_bounds__(256) gibbs_draw_kernel(GibbsDrawArgs a)
                 PhiloxF rs(a.seed, (uint32_t)f, (uint32_t)lane | 0x40000000u, a.sweep);
                 float lb;
                 const float x = rs.gamma_log((float)g, &lb);
-                lg = logf(x) + lb;
+                lg = __logf(x) + lb;
             }
             float mx = lg;
             for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-            const float e = lane < K ? expf(lg - mx) : 0.f;
+            const float e = lane < K ? __expf(lg - mx) : 0.f;
             float s = e;
             for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
             if (lane < KT) a.W[f * KT + lane] = e / s;
@@ -191,9 +191,9 @@ __global__ void __launch_bounds__(256) gibbs_draw_kernel(GibbsDrawArgs a)
                 const float y = rs.gamma_log((float)(a.beta + c0), &ly);
                 // H = x e^lx / (x e^lx + y e^ly) and 1 - H, each through the difference of the logarithms: no
                 // underflow for shapes << 1 and no cancellation in the complement when H is within 1e-8 of 1
-                const float dl = (logf(y) + ly) - (logf(x) + lx);
-                hv = fmaxf(1.0f / (1.0f + expf(dl)), 1e-30f);
-                cv = fmaxf(1.0f / (1.0f + expf(-dl)), 1e-30f);
+                const float dl = (__logf(y) + ly) - (__logf(x) + lx);
+                hv = fmaxf(__fdividef(1.0f, 1.0f + __expf(dl)), 1e-30f);
+                cv = fmaxf(__fdividef(1.0f, 1.0f + __expf(-dl)), 1e-30f);
             }
             a.HH[(a.N + n) * KT + k] = hv;
             a.HH[n * KT + k] = cv;

@@ -20,7 +20,7 @@ def relF(a, b):
     return np.linalg.norm(a - b) / np.linalg.norm(b)
 
 
-def _run(precision, planned, updates, checkpoints):
+def _run(precision, planned, updates, checkpoints, F=F, N=N, K=K, GAMMA=GAMMA):
     from nbmf_b200 import Engine
     e = Engine(precision=precision, planned_iters=planned)
     e.generate_synthetic(F, N, 8, 1.0, 1.0, 3)
@@ -61,3 +61,24 @@ def test_auto_precision_holds_the_gate_for_its_planned_updates():
             el = np.max(np.abs(lb[:i] - lb64[:i]) / np.abs(lb64[:i]))
             print(f"131072^2 K=128 AUTO planned {planned} (path {path}) after {i} updates: E_W {ew:.2e} E_H {eh:.2e} ELBO {el:.2e}")
             assert ew < 1e-5 and eh < 1e-5 and el < 1e-5, (planned, i, ew, eh, el)
+
+
+def test_auto_precision_holds_the_gate_at_config_4():
+    """BASELINE configs[3] at its size (65536 x 65536, K = 64): the variants `bench.py --workload c4` runs under AUTO
+    (25 planned updates -> hi + e5m2 lo; 15 -> hi only) against the FP64 path, for the whole plan."""
+    import torch
+    from nbmf_b200 import _lib
+    if torch.cuda.get_device_properties(0).total_memory < 60e9:
+        pytest.skip("needs a 180 GB class device")
+    Fc = Nc = 65536
+    Kc = 64
+    g = 1.0 / Kc
+    p64, ref, lb64 = _run(_lib.PREC_FP64, 0, 25, (15, 25), Fc, Nc, Kc, g)
+    assert p64 == _lib.PATH_FP64
+    for planned, want_path in ((15, _lib.PATH_TENSOR_FAST), (25, _lib.PATH_TENSOR_LO8)):
+        path, got, lb = _run(_lib.PREC_AUTO, planned, planned, (planned,), Fc, Nc, Kc, g)
+        assert path == want_path, (planned, path)
+        ew, eh = relF(got[planned][0], ref[planned][0]), relF(got[planned][1], ref[planned][1])
+        el = np.max(np.abs(lb[:planned] - lb64[:planned]) / np.abs(lb64[:planned]))
+        print(f"65536^2 K=64 AUTO planned {planned} (path {path}) after {planned} updates: E_W {ew:.2e} E_H {eh:.2e} ELBO {el:.2e}")
+        assert ew < 1e-5 and eh < 1e-5 and el < 1e-5, (planned, ew, eh, el)
