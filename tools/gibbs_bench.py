@@ -26,6 +26,8 @@ for (F, N, K, iters) in [(784, 60000, 16, 201), (8192, 65536, 16, 21), (8192, 65
     out.append(rec)
     print(json.dumps(rec), flush=True)
 # CPU reference (oracle collapsed sampler == the reference's own code draw for draw), bounded sample
+if os.environ.get("NBMF_LIB_VARIANT"):
+    sys.exit(0)   # variant runs: no CPU reference
 F, N, K = 784, 200, 16
 V, _, _ = oracle.generate(F, N, 8, 0.3, 1.5, 3)
 Z = oracle.random_labels(V, K, 4)
