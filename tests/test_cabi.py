@@ -72,3 +72,23 @@ def test_glue_sources_use_only_declared_entry_points():
         used = set(re.findall(r"\b(nbmf_[a-z0-9_]+)\s*\(", text)) - types
         used = {u for u in used if not u.startswith("nbmf_glue") and not u.startswith("nbmf_b200")}
         assert used <= declared, (rel, sorted(used - declared))
+
+
+def test_auto_precision_horizons_are_below_the_measured_ones():
+    """Host logic of NBMF_PREC_AUTO (tensor_pass.cu:tp_horizon): the planned-update horizon of each f16 variant, as a
+    function of the reduction length, stays below what profiles/r2_error_growth_*.log measured (hi only 16 / 23 / 31
+    updates at 16384^2 / 65536^2 / 262144^2, hi + lo 64 / 39 / 57), shrinks for short reductions and never exceeds the
+    reference's default iter = 100 (collapsed_gibbs_z_VB.cpp:376), so a default-length run is always FP64."""
+    from nbmf_b200 import _lib
+    lib = _lib.load()
+    hz = lambda path, n: lib.nbmf_debug_model_error(path, float(n), 0)
+    measured = {_lib.PATH_TENSOR_FAST: {16384: 16, 65536: 23, 262144: 31}, _lib.PATH_TENSOR_LO8: {16384: 64, 65536: 39, 262144: 57}}
+    for path, pts in measured.items():
+        for n, m in pts.items():
+            assert 0 < hz(path, n) <= m, (path, n, hz(path, n), m)
+        assert hz(path, 131072) <= max(hz(path, 65536), hz(path, 262144))
+        assert hz(path, 1024) < hz(path, 16384)
+        assert all(hz(path, n) < 100 for n in (512, 4096, 16384, 65536, 131072, 262144, 1 << 20))
+    assert hz(_lib.PATH_TENSOR_FAST, 262144) == 25      # the plan bench.py's default run executes (warm-up 5 + 20 steps)
+    assert hz(_lib.PATH_TENSOR, 65536) == hz(_lib.PATH_TENSOR_LO8, 65536)
+    assert hz(_lib.PATH_FP64, 65536) > 1e6               # no horizon: exact
