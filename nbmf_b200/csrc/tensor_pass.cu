@@ -37,7 +37,7 @@
 #include <cstdio>
 #include <cstdlib>
 
-#define TP_THREADS 640
+#define TP_THREADS 640       // 4 service warps + 4 epilogue warpgroups (TPCfg::THREADS: 768 where a fifth group runs)
 #ifndef TP_REGS_SERVICE
 #define TP_REGS_SERVICE 32   // 128 x (96 - 32) registers released ...
 #define TP_REGS_EPI 112      // ... 512 x (112 - 96) taken (the pool is the 640 x 96 of the launch)
@@ -727,8 +727,13 @@ struct TPCfg {
     static constexpr int STAGES = (224 * 1024 / TILE_BYTES) > 16 ? 16 : (224 * 1024 / TILE_BYTES);
     // S slots (fp32 stage-1 accumulators, 64 columns each).  The e5m2 copy of R needs 64 more TMEM
     // columns: at KP = 128 an S slot makes room (a step is longer there, two slots keep stage 1 fed).
+    // Epilogue warpgroups.  At KP = 64 a step carries half the tensor work but the same 64 reciprocals per lane, and the
+    // latency of a group's step sets the pace (tensor pipe 40 % busy, issue slots 49 %): a fifth group (768 threads, the
+    // registers re-divided with setmaxnreg: 40 per service thread, 88 per epilogue thread) takes every fifth step.
+    static constexpr int NG = (KP == 64 && !LO8) ? 5 : 4;
+    static constexpr int THREADS = 128 + 128 * NG;
     static constexpr int NS = (LO8 && KP == 128) ? 2 : ((KP == 64 && !LO8) ? 4 : 3);   // KP = 64 has TMEM to spare: a fourth slot
-    static constexpr int NR = 4;                            // R slots (f16 reciprocals, 32 columns each)
+    static constexpr int NR = NG;                           // R slots (f16 reciprocals, 32 columns each): one per group
     static constexpr int COL_G = 0;
     static constexpr int COL_S = KP;                        // + 64 * (step % NS)
     static constexpr int COL_R = KP + 64 * NS;              // + 32 * (step % NR)
@@ -742,7 +747,7 @@ struct TPCfg {
 };
 
 template <int KP, bool ROWS, bool WANT_LOG, bool HAS_NA, bool USE_LO, bool LO8>
-__global__ void __launch_bounds__(TP_THREADS, 1)
+__global__ void __launch_bounds__((TPCfg<KP, USE_LO, LO8>::THREADS), 1)
 tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__ CUtensorMap tmLo, TPArgs a)
 {
     using C = TPCfg<KP, USE_LO, LO8>;
@@ -751,9 +756,9 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
     const uint32_t bar_base = smem_base + C::STAGES * C::TILE_BYTES;
     auto BAR_FULL = [&](int s) { return bar_base + 8u * s; };
     auto BAR_EMPTY = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
-    // SFULL is indexed by step % 4 (= the epilogue group), not by S slot: a parity wait is only
+    // SFULL is indexed by step % NG (= the epilogue group), not by S slot: a parity wait is only
     // safe if the waiter cannot be two completions ahead, and a group knows that stage 1 of its
-    // previous step (gs-4), hence of every earlier step, has completed.
+    // previous step (gs-NG), hence of every earlier step, has completed.
     const uint32_t BAR_SFULL = bar_base + 8u * (2 * C::STAGES);      // [NR] stage 1 done          (commit)
     const uint32_t BAR_SFREE = BAR_SFULL + 8u * C::NR;                // [NS] epilogue has read S    (128 arrivals)
     const uint32_t BAR_RREADY = BAR_SFREE + 8u * C::NS;               // [NR] epilogue has written R (128 arrivals)
@@ -779,9 +784,9 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
         for (int s = 0; s < C::NS; s++) mbar_init(BAR_SFREE + 8u * s, 128);
         for (int s = 0; s < C::NR; s++) { mbar_init(BAR_SFULL + 8u * s, 1); mbar_init(BAR_RREADY + 8u * s, 128); mbar_init(BAR_RFREE + 8u * s, 1); }
         mbar_init(BAR_GFULL, 1);
-        mbar_init(BAR_GDRAIN, 512);
-        mbar_init(BAR_UREADY, 512);
-        for (int s = 0; s < 4; s++) { mbar_init(BAR_IFULL + 8u * s, 1); mbar_init(BAR_IEMPTY + 8u * s, 2 + 512); }
+        mbar_init(BAR_GDRAIN, 128 * C::NG);
+        mbar_init(BAR_UREADY, 128 * C::NG);
+        for (int s = 0; s < 4; s++) { mbar_init(BAR_IFULL + 8u * s, 1); mbar_init(BAR_IEMPTY + 8u * s, 2 + 128 * C::NG); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -813,7 +818,7 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
     // epilogue gains (measured: C4 5.07 -> 5.20 ms, C5 hi-only +1 %).
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if constexpr (C::NS == 2) reg_dealloc<TP_REGS_SERVICE>();
+        if constexpr (C::NG == 5) reg_dealloc<40>(); else if constexpr (C::NS == 2) reg_dealloc<TP_REGS_SERVICE>();
         if (elect_one()) {
             uint32_t stage = 0, phase = 0;
             PROF_DECL;
@@ -860,14 +865,14 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
         // (no indexed arrays) and descriptors are formed as {base_lo + constant, constant_hi}.
         // A wait on the parity *before* a barrier's first completion returns at once, which
         // covers the first use of every slot.
-        if constexpr (C::NS == 2) reg_dealloc<TP_REGS_SERVICE>();
+        if constexpr (C::NG == 5) reg_dealloc<40>(); else if constexpr (C::NS == 2) reg_dealloc<TP_REGS_SERVICE>();
         if (elect_one()) {
             constexpr uint32_t IDESC1 = make_idesc(128, C::STEP_ROWS, 0);
             constexpr uint32_t DHI = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO = 1024 B, version 1, SWIZZLE_128B
             constexpr uint32_t DLO1 = (16u >> 4) << 16;                    // K-major: LBO field = 1
             uint32_t s_stage = 0, s_phase = 0;   // smem ring position of the next tile to run stage 1 on
             uint32_t slot = 0, use_par = 0;      // S slot of the next step and parity of its use count
-            uint32_t g4 = 0;                     // step % 4: the epilogue group that takes the step
+            uint32_t g4 = 0;                     // step % NG: the epilogue group that takes the step
             uint32_t u_phase = 0, item_no = 0;
             PROF_DECL;
             for (int64_t w; (w = take_item(item_no, 12)) >= 0;) {
@@ -889,7 +894,7 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
                     const uint32_t lo = (((smem_base + s_stage * C::TILE_BYTES) >> 4) & 0x3FFFu) | DLO1;
                     const uint32_t d = tmem + C::COL_S + 64 * slot;
                     const uint32_t sfull = BAR_SFULL + 8u * g4;
-                    g4 = (g4 + 1u) & 3u;
+                    if (++g4 == (uint32_t)C::NG) g4 = 0;
                     if (++s_stage == C::STAGES) { s_stage = 0; s_phase ^= 1; }
                     if (++slot == C::NS) { slot = 0; use_par ^= 1u; }
                     // (two separate probes whose predicates are only combined at the top of the next
@@ -911,13 +916,13 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
         }
     } else if (warp == 3) {
         // ===================== MMA issuer, stage 2: G += R(slot gs%4) . (W_hi [+ W_lo]) =====================
-        if constexpr (C::NS == 2) reg_dealloc<TP_REGS_SERVICE>();
+        if constexpr (C::NG == 5) reg_dealloc<40>(); else if constexpr (C::NS == 2) reg_dealloc<TP_REGS_SERVICE>();
         if (elect_one()) {
             constexpr uint32_t IDESC2 = make_idesc(128, KP, 1);
             constexpr uint32_t DHI = (1024u >> 4) | (1u << 14) | (2u << 29);
             constexpr uint32_t DLO2 = ((uint32_t)C::BLOCK_BYTES >> 4) << 16; // MN-major: LBO = k-block stride
             uint32_t g_stage = 0;                // smem ring position of the next tile to run stage 2 on
-            uint32_t gs = 0;                     // global step counter
+            uint32_t rs_next = 0, rp_next = 0;   // R slot (= epilogue group) of the next step and parity of that slot's use count
             uint32_t u_phase = 0, item_no = 0, gd_phase = 0;
             PROF_DECL;
             for (int64_t w; (w = take_item(item_no, 13)) >= 0;) {
@@ -932,7 +937,7 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
                 int next_fold = a.sub_steps > 0 ? a.sub_steps : 0x7fffffff;   // first step of the next accumulation chain
                 PROF_ACC(0);
                 for (int t = 0; t < nst; t++) {
-                    const uint32_t rs = gs & 3u;
+                    const uint32_t rs = rs_next, rpar = rp_next;
                     bool fresh = (t == 0);
                     if (t == next_fold) {
                         // the chain that ended with step t-1 has been handed to the epilogue (commit below); G may only be
@@ -942,7 +947,7 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
                         next_fold += a.sub_steps;
                         fresh = true;
                     }
-                    if (!pre && !mbar_wait(BAR_RREADY + 8u * rs, (gs >> 2) & 1u, abort_flag, 4)) { ok = false; break; }
+                    if (!pre && !mbar_wait(BAR_RREADY + 8u * rs, rpar, abort_flag, 4)) { ok = false; break; }
                     tc_fence_after();
                     PROF_ACC(1);
                     // B operand MN-major (N = k contiguous) from the same smem tile stage 1 read K-major
@@ -951,8 +956,8 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
                     const uint32_t empty = BAR_EMPTY(g_stage);
                     const uint32_t g_stage_cur = g_stage; (void)g_stage_cur;
                     if (++g_stage == C::STAGES) g_stage = 0;
-                    gs++;
-                    pre = (t + 1 < nst) ? mbar_try(BAR_RREADY + 8u * (gs & 3u), (gs >> 2) & 1u) : 0u;
+                    if (++rs_next == (uint32_t)C::NG) { rs_next = 0; rp_next ^= 1u; }
+                    pre = (t + 1 < nst) ? mbar_try(BAR_RREADY + 8u * rs_next, rp_next) : 0u;
 #pragma unroll
                     for (int j = 0; j < C::STEP_ROWS / 16; j++)
                         tc_mma_ts2(tmem + C::COL_G, rcol + j * 8, lo + ((j * (16 * 128)) >> 4), DHI, IDESC2,
@@ -987,11 +992,11 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
             PROF_OUT(2);
         }
     } else if (warp == 2) {
-        if constexpr (C::NS == 2) reg_dealloc<TP_REGS_SERVICE>();   // (the TMEM allocator warp: setmaxnreg is a warpgroup-wide instruction)
+        if constexpr (C::NG == 5) reg_dealloc<40>(); else if constexpr (C::NS == 2) reg_dealloc<TP_REGS_SERVICE>();   // (the TMEM allocator warp: setmaxnreg is a warpgroup-wide instruction)
     } else {
         // ===================== epilogue =====================
-        if constexpr (C::NS == 2) reg_alloc<TP_REGS_EPI>();
-        // four warpgroups; group g owns R slot g and handles the steps with gs = g (mod 4).  More
+        if constexpr (C::NG == 5) reg_alloc<88>(); else if constexpr (C::NS == 2) reg_alloc<TP_REGS_EPI>();   // 768 x 80 at launch = 128 x 40 + 640 x 88
+        // NG (four or five) warpgroups; group g owns R slot g and handles the steps with gs = g (mod NG).  More
         // resident warps than the arithmetic needs: one step's epilogue (TMEM load -> select ->
         // rcp -> pack -> TMEM store -> mbarrier) lasts about two tensor steps.
         const int grp = (warp - 4) >> 2;            // = R slot
@@ -1010,6 +1015,7 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
         const uint32_t bar_sfull = BAR_SFULL + 8u * grp, bar_rready = BAR_RREADY + 8u * grp, bar_rfree = BAR_RFREE + 8u * grp;
         uint32_t g_phase = 0;
         uint32_t base = 0;                          // global step number of the item's first step
+        uint32_t base_mod = 0;                      // ... modulo the number of groups
         uint32_t r_par = 0;                         // parity of the use count of this group's R slot
         PROF_DECL;
         const float c0 = exp2f((float)(eU + eW - 14));
@@ -1087,14 +1093,14 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
             mbar_arrive(BAR_UREADY);
             first_item = false;
             prev_w = w;
-            // ---- steps with base + t = grp (mod 4)
+            // ---- steps with base + t = grp (mod NG)
             float log_acc = 0.f;
             const int64_t orow = ROWS ? l : (l >> 1);
             const uint32_t bsel = ROWS ? 0u : (uint32_t)(l & 1);
             // bits per step: ROWS: 32 n -> 1 word; COLS: 64 f -> 2 words.  Running pointers (one step of
-            // this group = 4 steps of the item) instead of an index product per step.
+            // this group = NG steps of the item) instead of an index product per step.
             constexpr int WPS = ROWS ? 1 : 2;
-            const int tfirst = (int)(((uint32_t)grp - base) & 3u);
+            const int tfirst = grp >= (int)base_mod ? grp - (int)base_mod : grp - (int)base_mod + C::NG;   // first step with base + t = grp (mod NG)
             const uint32_t *vp = a.vbits + orow * a.words + (t0 + tfirst) * WPS;
             const uint32_t *mp = a.mbits + orow * a.words + (t0 + tfirst) * WPS;
             uint32_t bv[WPS], bm[WPS];
@@ -1104,8 +1110,8 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
                     bv[i] = lane_ok ? __ldg(vp + i) : 0u;
                     bm[i] = HAS_NA ? (lane_ok ? __ldg(mp + i) : 0u) : 0xffffffffu;
                 }
-                vp += 4 * WPS;
-                if (HAS_NA) mp += 4 * WPS;
+                vp += C::NG * WPS;
+                if (HAS_NA) mp += C::NG * WPS;
             };
             if (tfirst < nst) load_bits();
             // accumulation chains of this item: [0, sub), [sub, 2 sub), ...; cur_chain = the one this group is in
@@ -1113,14 +1119,14 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
             const int n_chain = a.sub_steps > 0 ? (nst + sub - 1) / sub : 1;
             int cur_chain = 0;
             PROF_ACC(0);
-            for (int t = tfirst; t < nst && ok; t += 4) {
+            for (int t = tfirst; t < nst && ok; t += C::NG) {
                 uint32_t sel[WPS], vv[WPS];
 #pragma unroll
                 for (int i = 0; i < WPS; i++) {
                     vv[i] = bv[i];
                     sel[i] = ROWS ? bm[i] : ((bsel ? bv[i] : ~bv[i]) & bm[i]);
                 }
-                if (t + 4 < nst) load_bits();
+                if (t + C::NG < nst) load_bits();
                 const uint32_t gs = base + (uint32_t)t;
                 const uint32_t sslot = gs % (uint32_t)C::NS;
                 const uint32_t t_s = tmem + lane_addr + C::COL_S + 64 * sslot;
@@ -1201,7 +1207,7 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
                 if constexpr (C::NS == 2) {
                     uint32_t sa[64];
                     tc_ld64(t_s, sa);
-                    // stage 2 of step gs-4 must be done with the R slot: probe now, look at the answer later
+                    // stage 2 of step gs-NG must be done with the R slot: probe now, look at the answer later
                     rfree = mbar_try(bar_rfree, r_par ^ 1u);
                     tc_wait_ld();
                     tc_fence_before();
@@ -1251,6 +1257,7 @@ tp_pass_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__
             while (ok && cur_chain < n_chain - 1) { ok = fold_G(w, cur_chain > 0); cur_chain++; }
             prev_folded = n_chain > 1;
             base += (uint32_t)nst;
+            base_mod = (base_mod + (uint32_t)nst) % (uint32_t)C::NG;
             if (WANT_LOG) log_acc_total += (double)log_acc;
         }
         // ---- drain G of the last item
@@ -1301,7 +1308,7 @@ static cudaError_t launch_tp3(const CUtensorMap &tm, const CUtensorMap &tmlo, co
     using C = TPCfg<KP, USE_LO, LO8>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) return e;
-    kern<<<grid, TP_THREADS, C::SMEM_BYTES, st>>>(tm, tmlo, a);
+    kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(tm, tmlo, a);
     return cudaGetLastError();
 }
 // three precision variants: hi only (FAST), + W_lo in stage 2 as f16 (TENSOR) or as e5m2 (LO8)
