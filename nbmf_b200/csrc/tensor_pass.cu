@@ -1510,7 +1510,7 @@ extern "C" int nbmf_debug_tp_prof(unsigned long long *out64, int reset)
 }
 #endif
 
-// raw stage-1 accumulators of the first tile (tools/tp_probe.py); only a library built with
+// raw stage-1 accumulators of the first tile (tests/tools/tp_probe.py); only a library built with
 // EXTRA=-DTP_DEBUG_DUMP carries the dump code in the kernel
 extern "C" int nbmf_debug_tp_dump(nbmf_handle *h, int owner_rows, float *S_out, int *exps_out)
 {

@@ -24,7 +24,7 @@ sub = np.ascontiguousarray(m[:, :2000].T.astype(np.uint8))          # [n][f]
 np.savez_compressed(os.path.join(HERE, "mnistbinary_2000.npz"), bits=np.packbits(sub, axis=1, bitorder="little"),
                     shape=np.array([784, 2000]), density_full=np.array([m.mean()]))
 print("unvotes100 mean", np.nanmean(u), "mnist density", m.mean(), "subset", sub.mean())
-# all 60000 columns (BASELINE configs[2] at its size; 2 MB): tools/config3_gibbs.py
+# all 60000 columns (BASELINE configs[2] at its size; 2 MB): tests/tools/config3_gibbs.py
 full = np.ascontiguousarray(m.T.astype(np.uint8))
 np.savez_compressed(os.path.join(HERE, "mnistbinary_full.npz"), bits=np.packbits(full, axis=1, bitorder="little"),
                     shape=np.array([784, 60000]))

@@ -58,6 +58,13 @@ def test_product_package_never_uses_oracle():
             txt = open(os.path.join(dirpath, fn), errors="ignore").read()
             assert "import oracle" not in txt and "from oracle" not in txt, fn
             assert "oracle/" not in txt and "nbmf_oracle" not in txt and "libnbmf_ref" not in txt, fn
+    # the development tools and the reference-side glue do not use it either (the checker tools live in tests/tools/)
+    for sub in ("tools", "integration", "include"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, sub)):
+            for fn in files:
+                if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                    txt = open(os.path.join(dirpath, fn), errors="ignore").read()
+                    assert "import oracle" not in txt and "from oracle" not in txt and "nbmf_oracle" not in txt, (sub, fn)
 
 
 def test_glue_sources_use_only_declared_entry_points():

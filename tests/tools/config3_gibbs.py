@@ -6,10 +6,10 @@ Part A (parity, same data on both sides): the engine on the first 2000 columns -
 draw for draw to the reference's own code) on those columns: predictive log-likelihood per held-out pixel and the
 RMS difference of the posterior-mean E_V, beside the seed-to-seed spread of each side.
 Part B (the config at its size): the engine on all 60000 columns, per-seed predictive LL and sweep time.
-    python tools/config3_gibbs.py [sweeps] [ref_iters]      (ref_iters = 0: part B only)"""
+    python tests/tools/config3_gibbs.py [sweeps] [ref_iters]      (ref_iters = 0: part B only)"""
 import os, sys, time
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from nbmf_b200 import Engine, _lib
 from oracle import oracle
 from tests import datasets

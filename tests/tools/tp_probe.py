@@ -7,7 +7,7 @@ import sys
 import numpy as np
 import scipy.special as sp
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from nbmf_b200 import Engine, _lib  # noqa: E402
 from oracle import oracle  # noqa: E402
 

@@ -11,5 +11,5 @@ timeout 900 python tools/error_growth.py 65536 128 1,2,5,10,20,40,60,80,100 tens
 for p in 3 2 4; do
   timeout 600 python bench.py --workload c5 --precision $p --steps 5 --warmup 3 --no-e2e --no-cpu-baseline > $O/r2_bench_c5_p$p.json 2> $O/r2_bench_c5_p$p.err
 done
-timeout 600 python tools/gibbs_bench.py > $O/r2_gibbs_bench1.log 2>&1
+timeout 600 python tests/tools/gibbs_bench.py > $O/r2_gibbs_bench1.log 2>&1
 echo done

@@ -4,5 +4,5 @@ cd "$GRAFT_REPO_ROOT"
 O=gpurun_out
 timeout 600 python -m pytest tests/test_gpu_round2.py tests/test_gpu_entrypoints.py tests/test_gpu_configs.py tests/test_gpu_parity.py -m gpu -q -x --timeout=600 -k "gibbs or Gibbs or sample or config" > $O/r2_tests17.log 2>&1
 echo "pytest rc=$?" >> $O/r2_tests17.log
-timeout 300 python tools/gibbs_bench.py > $O/r2_gibbs_bench7.log 2>&1
+timeout 300 python tests/tools/gibbs_bench.py > $O/r2_gibbs_bench7.log 2>&1
 echo done

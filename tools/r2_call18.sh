@@ -6,7 +6,7 @@ O=gpurun_out
 timeout 1500 python -m pytest tests -m gpu -q --timeout=600 > $O/r2_gpu_tests_final.log 2>&1
 echo "pytest rc=$?" >> $O/r2_gpu_tests_final.log
 timeout 300 python __graft_entry__.py smoke > $O/r2_smoke_final.log 2>&1 || python -c "import __graft_entry__ as g; g.smoke()" > $O/r2_smoke_final.log 2>&1
-timeout 300 python tools/gibbs_bench.py > $O/r2_gibbs_bench_final.log 2>&1
+timeout 300 python tests/tools/gibbs_bench.py > $O/r2_gibbs_bench_final.log 2>&1
 timeout 900 python bench.py --steps 20 --warmup 5 > $O/r2f_bench_c5_auto.json 2> $O/r2f_bench_c5_auto.err
 timeout 600 python bench.py --precision 4 --steps 20 --warmup 5 --no-e2e --no-cpu-baseline > $O/r2f_bench_c5_lo8.json 2> $O/r2f_bench_c5_lo8.err
 timeout 600 python bench.py --precision 2 --steps 10 --warmup 3 --no-e2e --no-cpu-baseline > $O/r2f_bench_c5_hilo.json 2> $O/r2f_bench_c5_hilo.err

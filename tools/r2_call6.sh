@@ -6,7 +6,7 @@ O=gpurun_out
 export NBMF_TP_SPIN_LIMIT=2000000000
 timeout 900 python -m pytest tests -m gpu -q -x --timeout=600 > $O/r2_tests6.log 2>&1
 timeout 600 python tools/smallk_bench.py > $O/r2_smallk.log 2>&1
-timeout 300 python tools/gibbs_bench.py > $O/r2_gibbs_bench2.log 2>&1
+timeout 300 python tests/tools/gibbs_bench.py > $O/r2_gibbs_bench2.log 2>&1
 B="python bench.py --workload c5 --steps 2 --warmup 3 --no-e2e --no-cpu-baseline"
 $B > $O/r2_plain_c5.log 2>&1 && timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -s 40 -c 160 --csv --log-file $O/r2_launches_c5.csv $B > $O/r2_ncu_l_c5.log 2>&1
 $B --precision 4 > $O/r2_plain_c5_lo8.log 2>&1 && timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -s 40 -c 160 --csv --log-file $O/r2_launches_c5_lo8.csv $B --precision 4 > $O/r2_ncu_l_c5_lo8.log 2>&1

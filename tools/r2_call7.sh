@@ -10,5 +10,5 @@ for p in 3 4; do
   NBMF_TP_SUB_STEPS=0 timeout 600 python bench.py --workload c5 --precision $p --steps 10 --warmup 3 --no-e2e --no-cpu-baseline > $O/r2_bench_c5_p${p}_nofold.json 2> $O/r2_bench_c5_p${p}_nofold.err
 done
 timeout 300 python bench.py --workload c4 --precision 4 --steps 10 --warmup 3 --no-e2e --no-cpu-baseline > $O/r2_bench_c4_p4_fold.json 2>/dev/null
-timeout 1500 python tools/config3_gibbs.py 2000 400 > $O/r2_config3_gibbs.log 2>&1
+timeout 1500 python tests/tools/config3_gibbs.py 2000 400 > $O/r2_config3_gibbs.log 2>&1
 echo done

@@ -8,7 +8,7 @@ for p in 3 4; do
   timeout 600 python bench.py --workload c5 --precision $p --steps 10 --warmup 3 --no-e2e --no-cpu-baseline > $O/r2_bench_c5_p${p}_fold2.json 2> $O/r2_bench_c5_p${p}_fold2.err
 done
 NBMF_TP_SUB_STEPS=0 timeout 600 python bench.py --workload c5 --precision 4 --steps 10 --warmup 3 --no-e2e --no-cpu-baseline > $O/r2_bench_c5_p4_nofold2.json 2>/dev/null
-timeout 300 python tools/gibbs_bench.py > $O/r2_gibbs_bench3.log 2>&1
+timeout 300 python tests/tools/gibbs_bench.py > $O/r2_gibbs_bench3.log 2>&1
 timeout 300 python tools/error_growth.py 65536 128 1,20,40 lo8 > $O/r2_eg_64k_fold2.log 2>&1
 export NBMF_TP_SPIN_LIMIT=2000000000
 S="python tools/smallk_bench.py quick shapes=2,4,5 iters=2"
