@@ -110,13 +110,16 @@ def test_tensor_variants_vs_oracle(prec_name, F, N, K):
 # ---------------------------------------------------------------------------
 # Gibbs: the accumulation is deterministic given the labels; fast and wide kernels sample the same posterior
 # ---------------------------------------------------------------------------
-@pytest.mark.parametrize("K", [3, 10, 16, 40])
-def test_gibbs_rao_blackwell_means_of_a_fixed_label_matrix(K):
+@pytest.mark.parametrize("K,F,N,na", [(3, 90, 130, 0.15), (5, 90, 130, 0.15), (10, 90, 130, 0.15), (16, 90, 130, 0.15),
+                                      (24, 90, 130, 0.15), (32, 90, 130, 0.15), (40, 90, 130, 0.15),
+                                      (16, 200, 333, 0.0), (8, 31, 65, 0.0), (32, 70, 63, 0.0), (4, 300, 2, 0.3)])
+def test_gibbs_rao_blackwell_means_of_a_fixed_label_matrix(K, F, N, na):
     """iter = 2, burnin = 0: one sweep, kept; E_W / E_H are the means implied by that sweep's counts, i.e.
-    expectation.GibbsDirBer (R/generic_Gibbs_DirBer.R:82-90) of the returned Z_last -- deterministic."""
+    expectation.GibbsDirBer (R/generic_Gibbs_DirBer.R:82-90) of the returned Z_last -- deterministic.  Every
+    instantiation of the sweep kernel (KT = 4, 8, 16, 32, masked and unmasked; the wide kernel for K > 32), ragged
+    row and column counts, fewer rows than a warp, fewer columns than a Philox block."""
     from nbmf_b200 import Engine, _lib
-    F, N = 90, 130
-    V, Z = _problem(F, N, K, 0.15, 13)
+    V, Z = _problem(F, N, K, na, 13)
     e = Engine(precision=_lib.PREC_FP64)
     e.set_data(V); e.init_from_labels(Z, K)
     EW, EH, _, Zl = e.gibbs_dirber(K, 1.2, 0.8, 0.3, iter=2, burnin=0.0, seed=5, want_Z=True)
