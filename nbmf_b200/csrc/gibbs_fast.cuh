@@ -282,13 +282,8 @@ __global__ void __launch_bounds__(32 * GIBBS_WMAX, KT > 16 ? 2 : GIBBS_MINB16) g
     }
     const int mis = (int)(a.n_offset & 3);                // sub-tiles start at multiples of NB: only a misaligned shard start shifts the Philox blocks
     const uint32_t pk1 = (uint32_t)(a.seed >> 32) ^ 0x2545F491u;
-    for (int st = 0; st < a.ct; st++) {
-        const int64_t n0 = ((int64_t)blockIdx.x * a.ct + st) * NB;
-        if (n0 >= a.N) break;                             // block-uniform
-        const int nb = (int)min((int64_t)NB, a.N - n0);
-        // (No barrier here: the previous sub-tile's tables were last read before its post-phase-1 barrier, its keys before
-        // the post-phase-2 barrier, and its counters are read below by the loop that ran right after that barrier; all
-        // three are next written behind at least one more barrier.  The table build overlaps the count output.)
+    // tables and bit words of the sub-tile that starts at column n0 (nb columns of it exist)
+    auto build_tables = [&](const int64_t n0, const int nb) {
         // the four tables of every column pair from four loads: (H or 1-H of column j, H or 1-H of column j+1)
         for (int i = tid; i < (NB / 2) * KT; i += nthreads) {
             const int j = 2 * (i / KT), k = i % KT;
@@ -311,7 +306,20 @@ __global__ void __launch_bounds__(32 * GIBBS_WMAX, KT > 16 ? 2 : GIBBS_MINB16) g
             sV[i] = in ? __ldg(a.vc + (n0 + j) * a.Fw + wrd) : 0u;
             if (MASKED) sM[i] = in ? __ldg(a.mc + (n0 + j) * a.Fw + wrd) : 0u;
         }
-        __syncthreads();
+    };
+    // Two barriers per sub-tile: [phase 1] | [phase 2 + tables of the next sub-tile] | [count output, then phase 1 of the
+    // next sub-tile without a barrier].  Hazards: the tables were last read in phase 1 (before the first barrier); the key
+    // tile is rewritten by the next phase 1, after the second barrier that ends phase 2; the counters are zeroed by the
+    // output loop, which every thread runs before its next phase 1 and hence before the next first barrier and phase 2.
+    {
+        const int64_t n00 = (int64_t)blockIdx.x * a.ct * NB;
+        if (n00 < a.N) build_tables(n00, (int)min((int64_t)NB, a.N - n00));
+    }
+    __syncthreads();                                      // the first tables, the zeroed histograms
+    for (int st = 0; st < a.ct; st++) {
+        const int64_t n0 = ((int64_t)blockIdx.x * a.ct + st) * NB;
+        if (n0 >= a.N) break;                             // block-uniform
+        const int nb = (int)min((int64_t)NB, a.N - n0);
         // ---- phase 1: thread = row, four columns (one Philox block, two column pairs) per iteration.  Columns beyond
         //      the matrix have no bits and all-zero tables: they are sampled like the rest and never counted.
         for (int j0 = 0; j0 < nb; j0 += 4) {
@@ -401,6 +409,7 @@ __global__ void __launch_bounds__(32 * GIBBS_WMAX, KT > 16 ? 2 : GIBBS_MINB16) g
                 }
             }
         }
+        if (st + 1 < a.ct && n0 + NB < a.N) build_tables(n0 + NB, (int)min((int64_t)NB, a.N - n0 - NB));
         __syncthreads();
         // column-side counts of the sub-tile out to (2n + bit, label); clear for the next one
         for (int i = tid; i < NB * KEYS; i += nthreads) {
