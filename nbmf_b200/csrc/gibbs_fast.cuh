@@ -6,7 +6,7 @@
 //                        expectation.GibbsDirBer (R/generic_Gibbs_DirBer.R:82-90) for a kept sweep,
 //                        and draws W_f ~ Dir(gamma + n_total_f), H_nk ~ Beta(alpha + ones, beta + zeros)
 //                        (samples_VWH_DirBer, collapsed_gibbs_z.cpp:589-605)
-//   gibbs_sweep_kt_kernel Z_fn ~ Cat(W_fk H_nk^v (1 - H_nk)^(1-v)) for a (256 rows x NB columns) tile per
+//   gibbs_sweep_kt_kernel Z_fn ~ Cat(W_fk H_nk^v (1 - H_nk)^(1-v)) for a (32 x warps rows x NB columns) tile per
 //                        block (R/MCEM - sample_gibbs.R:62-71 conditional, sample_gibbs.cpp:43 likelihood
 //                        form) and the tile's counts
 //
@@ -19,14 +19,17 @@
 //   * one Philox4x32-10 block serves four consecutive columns (keyed seed; f, n/4, sweep)
 //   * single pass: the K running sums c_k are kept in registers, the draw is #{k : c_k <= u c_K}, counted as the
 //     sum of K-1 compare results (FSET.BF, added in fp32 pairs)
-//   * row-side counts: the lane owns its row, so its histogram is a private shared-memory column (no
-//     shared-memory atomics) that leaves once per block as one integer atomic per (row, label);
+//   * row-side counts: the lane owns its row; its histogram is a column of 16-bit counters in shared memory (two
+//     lanes per word), bumped by a no-return shared atomic (no load -> add -> store chain), and leaves once per
+//     block as one integer atomic per (row, label);
 //   * column-side counts: every entry leaves its (label, bit) key as a byte in a shared-memory tile; after a
-//     barrier the block turns by 90 degrees -- thread = column (x row group) -- and counts its column's keys in
-//     a private shared-memory histogram column (bank = thread, no atomics).  [The first version counted with
-//     2K ballots per warp and column: 128 of its ~210 warp instructions per 32 entries at K = 16.]  The totals
-//     leave as plain stores into the row tile's partial buffer cNp [f tiles][2N][KT], which gibbs_draw_kernel
-//     sums, or as integer atomics when there are many row tiles.
+//     barrier the block turns by 90 degrees -- thread = column (x row group) -- and adds its column's keys into
+//     hC[key][column] with shared atomics: the bank is the column whatever the key, so a warp's 32 columns never
+//     conflict.  [History: 2K ballots per warp and column were 128 of ~210 warp instructions per 32 entries at
+//     K = 16; private 16-bit histograms per thread had random 4-way bank conflicts.]  The totals leave as plain
+//     stores into the row tile's partial buffer cNp [f tiles][2N][KT], which gibbs_draw_kernel sums, or as
+//     integer atomics when there are many row tiles.
+//   * two barriers per 64-column sub-tile: the next sub-tile's tables are built beside phase 2
 // Integer counts only, so the result does not depend on the order of the atomics.
 #pragma once
 #include "common.cuh"
